@@ -1,0 +1,98 @@
+// Shared declarations of the hetmogp_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/hetmogp_b200.h"
+
+#define HM_MAXQ HMOGP_MAX_Q
+#define HM_MAXT HMOGP_MAX_TASKS
+#define HM_MAXJ HMOGP_MAX_J
+#define HM_MAXF HMOGP_MAX_DIMF
+#define HM_MAXXD 4
+
+void hm_set_error(const char* fmt, ...);
+
+#define HM_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            hm_set_error("%s:%d CUDA error: %s (%s)", __FILE__, __LINE__, cudaGetErrorString(_e), #call); \
+            return HMOGP_ERR_CUDA;                                                             \
+        }                                                                                      \
+    } while (0)
+
+#define HM_CHECK(call)                 \
+    do {                               \
+        int _r = (call);               \
+        if (_r != 0) return _r;        \
+    } while (0)
+
+static inline int64_t hm_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Per-step scalar constants, filled on the device by hm_prep_consts (no host round trip).
+struct HmConsts {
+    double var[HM_MAXQ];     // sigma_q^2
+    double ls[HM_MAXQ];      // l_q
+    double inv_l2[HM_MAXQ];  // 1/l_q^2
+    double W[HM_MAXJ][HM_MAXQ];
+    double kappa[HM_MAXJ][HM_MAXQ];
+    double Wc[HM_MAXJ][HM_MAXQ];  // chain multipliers (quirk C-5), = W by default
+    double kc[HM_MAXJ][HM_MAXQ];
+    double kdiag[HM_MAXJ];        // sum_q (W_dq^2 + kappa_dq) sigma_q^2   (util.py:178 diagonal)
+    double bscale[HM_MAXT];
+};
+
+// Task table shared by the N-sized kernels.
+struct HmTasks {
+    int T, Q, Xdim, J;
+    int kind[HM_MAXT], K[HM_MAXT], dimf[HM_MAXT], foff[HM_MAXT];
+    double sigma[HM_MAXT];
+    const double* X[HM_MAXT];  // [N_t, Xdim] resident fp64 rows
+    const double* Y[HM_MAXT];  // [N_t]
+    int64_t begin[HM_MAXT];    // active slice
+    int64_t count[HM_MAXT];
+    void* AC[HM_MAXT];         // [count, 2Q]  a_tq, c_tq          (compute type)
+    void* MW[HM_MAXT];         // [count, 4Q]  mu, omega, mu_c, omega_c (compute type)
+};
+
+// ---------------------------------------------------------------- M x M fp64 algebra (mm_algebra.cu)
+// Row-major, leading dimension ld, batch of Q matrices with stride sQ.
+int hm_dgemm(cudaStream_t s, bool ta, bool tb, int M, int N, int K, double alpha, const double* A, int lda, int64_t sA,
+             const double* B, int ldb, int64_t sB, double beta, double* C, int ldc, int64_t sC, int batch,
+             int nsub = 1, int64_t subA = 0, int64_t subB = 0, int64_t subC = 0, bool lower_only = false);
+int hm_cholesky(cudaStream_t s, double* A, int Mp, int64_t sQ, int Q, int* flags);       // in place, lower
+int hm_tri_inverse(cudaStream_t s, const double* L, double* X, double* tmp, int Mp, int64_t sQ, int Q);
+int hm_build_kuu(cudaStream_t s, const double* Zp, const HmConsts* c, const double* jitter, double* Kuu, int M, int Mp,
+                 int Xdim, int Q);
+
+// ---------------------------------------------------------------- likelihood kernels (lik_kernels.cu)
+struct HmLikStatsLayout {
+    int per_task;  // doubles per task in the partial/stat block: [VE, nneg, sdv[F], sma[F][Q], svc[F][Q]]
+};
+int hm_lik_rows(cudaStream_t s, int prec, const HmTasks& tk, const HmConsts* consts, int t, bool want_grads,
+                bool has_chain, double* partials, int max_blocks, int* nblocks_out, double* rows_m, double* rows_v,
+                double* rows_ve, double* rows_dm, double* rows_dv);
+int hm_lik_var_exp(cudaStream_t s, int prec, const hmogp_lik_desc& lik, int64_t N, const double* Y, const double* Mf,
+                   const double* Vf, double* VE, double* dm, double* dv);
+int hm_lik_pointwise(cudaStream_t s, const hmogp_lik_desc& lik, int64_t N, const double* F, const double* Y,
+                     double* logp, double* dlogp, double* d2logp);
+int hm_upload_gh_tables();
+
+// ---------------------------------------------------------------- N-sized SIMT contractions (proj_simt.cu, gram_simt.cu)
+struct HmProjArgs {
+    int M, Mp, Mc, Q, Xdim;
+    const double* Zp;      // [Q][Mp][Xdim] padded inducing inputs
+    const double* alpha;   // [Q][Mp]
+    const void* C;         // [Q][Mp][Mp] in the compute type
+    const HmConsts* consts;
+    double* colpart;       // bwd: [Q][nworkers][ (1+Xdim)*Mc + 1 ]
+    int nworkers;
+};
+int hm_proj_fwd(cudaStream_t s, int prec, const HmTasks& tk, const HmProjArgs& a);
+int hm_proj_bwd(cudaStream_t s, int prec, const HmTasks& tk, const HmProjArgs& a, bool hyper);
+int hm_proj_workers(int prec, int Mc);
+int hm_gram(cudaStream_t s, int prec, const HmTasks& tk, const HmProjArgs& a, double* Hpart, int nsplit);
+int hm_gram_splits(int prec, int Mc, int Q);

@@ -1,0 +1,274 @@
+// W-mix + heterogeneous-likelihood Gauss-Hermite kernels.
+//
+//  hm_lik_rows     per data row of task t: LMC mix of the per-latent projections (a_tq, c_tq) into the output
+//                  functions' posterior mean/variance (svmogp_inf.py:54-65,216-218 via SURVEY App. B), var_exp and
+//                  var_exp_derivatives of the task's likelihood (svmogp_inf.py:73-78, het_likelihood.py:101-131),
+//                  the mixed row weights mu_tq / omega_tq for the backward contractions, and block-reduced fp64
+//                  partial sums of everything that is a scalar statistic.
+//  hm_lik_var_exp  the stand-alone plug-in: likelihoods/<name>.py var_exp + var_exp_derivatives on given (Y, M, V).
+//  hm_lik_pointwise  logpdf / dlogp_df / d2logp_df2 at given F.
+#include <math_constants.h>
+
+#include "gh_tables.h"
+#include "likelihoods.cuh"
+
+int hm_upload_gh_tables() {
+    static int done_for_device[64] = {0};
+    int dev = 0;
+    HM_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && done_for_device[dev]) return 0;
+    const double sqrt_pi = 1.7724538509055160273;  // == numpy.sqrt(numpy.pi)
+    double w20[20], w10[10];
+    for (int i = 0; i < 20; ++i) w20[i] = HMOGP_GH20_W[i] / sqrt_pi;
+    for (int i = 0; i < 10; ++i) w10[i] = HMOGP_GH10_W[i] / sqrt_pi;
+    HM_CUDA(cudaMemcpyToSymbol(c_gh20_x, HMOGP_GH20_X, sizeof(double) * 20));
+    HM_CUDA(cudaMemcpyToSymbol(c_gh20_w, w20, sizeof(double) * 20));
+    HM_CUDA(cudaMemcpyToSymbol(c_gh10_x, HMOGP_GH10_X, sizeof(double) * 10));
+    HM_CUDA(cudaMemcpyToSymbol(c_gh10_w, w10, sizeof(double) * 10));
+    if (dev >= 0 && dev < 64) done_for_device[dev] = 1;
+    return 0;
+}
+
+#define HM_LIK_THREADS 128
+#define HM_LIK_MAXSTAT (2 + HM_MAXF * (1 + 2 * HM_MAXQ))
+
+struct HmLikRowArgs {
+    int kind, K, dimf, foff, Q, t;
+    double sigma;
+    int64_t count, begin;
+    const double* Y;
+    const void* AC;
+    void* MW;
+    const HmConsts* consts;
+    double* partials;  // [gridDim.x][nstat]
+    int want_grads, has_chain;
+    double *rows_m, *rows_v, *rows_ve, *rows_dm, *rows_dv;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(HM_LIK_THREADS) lik_rows_kernel(HmLikRowArgs p) {
+    __shared__ double sacc[HM_LIK_MAXSTAT];
+    const int nstat = 2 + p.dimf * (1 + 2 * p.Q);
+    for (int i = threadIdx.x; i < nstat; i += blockDim.x) sacc[i] = 0.0;
+    __syncthreads();
+    const HmConsts* __restrict__ cs = p.consts;
+    const int Q = p.Q, F = p.dimf;
+    const T bs = T(cs->bscale[p.t]);
+    double st[HM_LIK_MAXSTAT];
+    for (int i = 0; i < nstat; ++i) st[i] = 0.0;
+
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < p.count;
+         row += (int64_t)gridDim.x * blockDim.x) {
+        const T* ac = reinterpret_cast<const T*>(p.AC) + row * 2 * Q;
+        T a[HM_MAXQ], c[HM_MAXQ];
+        for (int q = 0; q < Q; ++q) { a[q] = ac[q]; c[q] = ac[Q + q]; }
+        T m[HM_MAXF], v[HM_MAXF];
+        int nneg = 0;
+        for (int f = 0; f < F; ++f) {
+            const int d = p.foff + f;
+            T mm = 0, vv = T(cs->kdiag[d]);
+            for (int q = 0; q < Q; ++q) {
+                const T w = T(cs->W[d][q]);
+                mm += w * a[q];
+                vv += w * w * c[q];
+            }
+            m[f] = mm;
+            v[f] = vv;
+            nneg += (vv < T(0)) ? 1 : 0;
+        }
+        const T y = T(p.Y[p.begin + row]);
+        HmLikOut<T> o;
+        hm_lik_eval<T>(p.kind, p.K, T(p.sigma), y, m, v, o);
+        o.ve *= bs;
+        for (int f = 0; f < F; ++f) { o.dm[f] *= bs; o.dv[f] *= bs; }
+        st[0] += (double)o.ve;
+        st[1] += (double)nneg;
+        for (int f = 0; f < F; ++f) {
+            double* sf = st + 2 + f * (1 + 2 * Q);
+            sf[0] += (double)o.dv[f];
+            for (int q = 0; q < Q; ++q) {
+                sf[1 + q] += (double)(o.dm[f] * a[q]);
+                sf[1 + Q + q] += (double)(o.dv[f] * c[q]);
+            }
+        }
+        if (p.want_grads) {
+            T* mw = reinterpret_cast<T*>(p.MW) + row * 4 * Q;
+            for (int q = 0; q < Q; ++q) {
+                T mu = 0, om = 0, muc = 0, omc = 0;
+                for (int f = 0; f < F; ++f) {
+                    const int d = p.foff + f;
+                    const T w = T(cs->W[d][q]), wc = T(cs->Wc[d][q]);
+                    mu += w * o.dm[f];
+                    om += w * w * o.dv[f];
+                    muc += wc * o.dm[f];
+                    omc += wc * w * o.dv[f];
+                }
+                mw[q] = mu;
+                mw[Q + q] = om;
+                mw[2 * Q + q] = muc;
+                mw[3 * Q + q] = omc;
+            }
+        }
+        if (p.rows_m) {
+            for (int f = 0; f < F; ++f) {
+                p.rows_m[row * F + f] = (double)m[f];
+                p.rows_v[row * F + f] = (double)v[f];
+                p.rows_dm[row * F + f] = (double)o.dm[f];
+                p.rows_dv[row * F + f] = (double)o.dv[f];
+            }
+            p.rows_ve[row] = (double)o.ve;
+        }
+    }
+    // block reduction: warp shuffles then one shared-memory atomic per warp and statistic
+    for (int i = 0; i < nstat; ++i) {
+        double x = st[i];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[i], x);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nstat; i += blockDim.x) p.partials[(int64_t)blockIdx.x * nstat + i] = sacc[i];
+}
+
+int hm_lik_rows(cudaStream_t s, int prec, const HmTasks& tk, const HmConsts* consts, int t, bool want_grads,
+                bool has_chain, double* partials, int max_blocks, int* nblocks_out, double* rows_m, double* rows_v,
+                double* rows_ve, double* rows_dm, double* rows_dv) {
+    HmLikRowArgs p;
+    p.kind = tk.kind[t]; p.K = tk.K[t]; p.dimf = tk.dimf[t]; p.foff = tk.foff[t]; p.Q = tk.Q; p.t = t;
+    p.sigma = tk.sigma[t];
+    p.count = tk.count[t]; p.begin = tk.begin[t];
+    p.Y = tk.Y[t]; p.AC = tk.AC[t]; p.MW = tk.MW[t];
+    p.consts = consts; p.partials = partials;
+    p.want_grads = want_grads ? 1 : 0; p.has_chain = has_chain ? 1 : 0;
+    p.rows_m = rows_m; p.rows_v = rows_v; p.rows_ve = rows_ve; p.rows_dm = rows_dm; p.rows_dv = rows_dv;
+    int64_t nb = hm_cdiv(p.count, HM_LIK_THREADS);
+    if (nb > max_blocks) nb = max_blocks;
+    if (nb < 1) nb = 1;
+    *nblocks_out = (int)nb;
+    if (prec == HMOGP_PREC_FP64) lik_rows_kernel<double><<<(unsigned)nb, HM_LIK_THREADS, 0, s>>>(p);
+    else lik_rows_kernel<float><<<(unsigned)nb, HM_LIK_THREADS, 0, s>>>(p);
+    HM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ stand-alone var_exp
+template <typename T>
+__global__ void __launch_bounds__(HM_LIK_THREADS) lik_varexp_kernel(int kind, int K, double sigma, int F, int64_t N,
+                                                                    const double* __restrict__ Y,
+                                                                    const double* __restrict__ Mf,
+                                                                    const double* __restrict__ Vf, double* VE,
+                                                                    double* dm, double* dv) {
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < N; row += (int64_t)gridDim.x * blockDim.x) {
+        T m[HM_MAXF], v[HM_MAXF];
+        for (int f = 0; f < F; ++f) { m[f] = T(Mf[row * F + f]); v[f] = T(Vf[row * F + f]); }
+        HmLikOut<T> o;
+        hm_lik_eval<T>(kind, K, T(sigma), T(Y[row]), m, v, o);
+        if (VE) VE[row] = (double)o.ve;
+        for (int f = 0; f < F; ++f) {
+            if (dm) dm[row * F + f] = (double)o.dm[f];
+            if (dv) dv[row * F + f] = (double)o.dv[f];
+        }
+    }
+}
+
+static int lik_dimf(const hmogp_lik_desc& lik) {
+    switch (lik.kind) {
+        case HMOGP_LIK_HETGAUSSIAN: case HMOGP_LIK_GAMMA: case HMOGP_LIK_BETA: return 2;
+        case HMOGP_LIK_CATEGORICAL: return lik.K - 1;
+        default: return 1;
+    }
+}
+
+int hm_lik_var_exp(cudaStream_t s, int prec, const hmogp_lik_desc& lik, int64_t N, const double* Y, const double* Mf,
+                   const double* Vf, double* VE, double* dm, double* dv) {
+    if (N <= 0) return 0;
+    const int F = lik_dimf(lik);
+    int64_t nb = hm_cdiv(N, HM_LIK_THREADS);
+    if (nb > 148 * 16) nb = 148 * 16;
+    if (prec == HMOGP_PREC_FP64)
+        lik_varexp_kernel<double><<<(unsigned)nb, HM_LIK_THREADS, 0, s>>>(lik.kind, lik.K, lik.sigma, F, N, Y, Mf, Vf, VE, dm, dv);
+    else
+        lik_varexp_kernel<float><<<(unsigned)nb, HM_LIK_THREADS, 0, s>>>(lik.kind, lik.K, lik.sigma, F, N, Y, Mf, Vf, VE, dm, dv);
+    HM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ pointwise (fp64)
+__global__ void __launch_bounds__(HM_LIK_THREADS) lik_pointwise_kernel(int kind, int K, double sigma, int F, int64_t N,
+                                                                       const double* __restrict__ Fv,
+                                                                       const double* __restrict__ Y, double* logp,
+                                                                       double* dlogp, double* d2logp) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= N) return;
+    const double y = Y[row];
+    const double* f = Fv + row * F;
+    double lp = 0.0, d1[HM_MAXF], d2[HM_MAXF];
+    for (int i = 0; i < HM_MAXF; ++i) { d1[i] = 0.0; d2[i] = 0.0; }
+    if (kind == HMOGP_LIK_GAUSSIAN) {
+        // gaussian.py:33: logpdf uses unit variance (quirk C-9); derivatives are not defined by the reference for
+        // the analytic Gaussian -- we return those of the sigma-noise model used by var_exp.
+        lp = -0.5 * log(2.0 * CUDART_PI) - 0.5 * (y - f[0]) * (y - f[0]);
+        d1[0] = (y - f[0]) / (sigma * sigma);
+        d2[0] = -1.0 / (sigma * sigma);
+    } else if (kind == HMOGP_LIK_HETGAUSSIAN) {
+        // hetgaussian.py:29-33 (logpdf only; the reference defines no dlogp_df for the analytic likelihoods)
+        const double evar = hm_safe_exp(f[1]);
+        const double prec = 1.0 / evar;
+        const double r = y - f[0];
+        lp = -0.5 * log(2.0 * CUDART_PI) - 0.5 * f[1] - 0.5 * (r * r) / evar;
+        d1[0] = prec * r; d1[1] = 0.5 * (prec * r * r - 1.0);
+        d2[0] = -prec; d2[1] = -0.5 * prec * r * r;
+    } else if (kind == HMOGP_LIK_BERNOULLI || kind == HMOGP_LIK_POISSON || kind == HMOGP_LIK_EXPONENTIAL) {
+        const double lgy1 = (kind == HMOGP_LIK_POISSON) ? lgamma(y + 1.0) : 0.0;
+        hm_point_1d<double>(kind, f[0], y, lgy1, lp, d1[0], d2[0]);
+    } else if (kind == HMOGP_LIK_CATEGORICAL) {
+        const int D = K - 1;
+        const int label = (int)y;
+        const bool valid = ((double)label == y) && label >= 1 && label <= K;
+        double e[HM_MAXF], den = 1.0;
+        for (int d = 0; d < D; ++d) { e[d] = hm_safe_exp(f[d]); den += e[d]; }
+        const double inv = 1.0 / den;
+        double psum = hm_clip(inv, 1e-9, 1.0 - 1e-9), py = psum;
+        for (int d = 0; d < D; ++d) {
+            const double pk = hm_clip(e[d] * inv, 1e-9, 1.0 - 1e-9);
+            psum += pk;
+            if (label == d + 1) py = pk;
+        }
+        lp = valid ? log(py / psum) : -CUDART_INF;
+        for (int d = 0; d < D; ++d) {
+            d1[d] = valid ? ((label == d + 1 ? 1.0 : 0.0) - 1.0) : 0.0;
+            d2[d] = valid ? -(e[d] * (den - e[d])) * inv * inv : 0.0;
+        }
+    } else {
+        const double a = hm_clip(hm_safe_exp(f[0]), 1e-9, 1e9), b = hm_clip(hm_safe_exp(f[1]), 1e-9, 1e9);
+        const double logy = log(y);
+        if (kind == HMOGP_LIK_GAMMA) {
+            const double psa = hm_digamma(a), tra = hm_trigamma(a), lb = log(b);
+            lp = -lgamma(a) + a * lb + (a - 1.0) * logy - b * y;
+            d1[0] = (-psa + lb + logy) * a; d1[1] = a - b * y;
+            d2[0] = (-psa - a * tra + lb + logy) * a; d2[1] = -y * b;
+        } else {
+            const double log1y = log(1.0 - y), ab = a + b;
+            const double psab = hm_digamma(ab), trab = hm_trigamma(ab), psa = hm_digamma(a), psb = hm_digamma(b);
+            lp = (a - 1.0) * logy + (b - 1.0) * log1y - (lgamma(a) + lgamma(b) - lgamma(ab));
+            d1[0] = (psab - psa + logy) * a; d1[1] = (psab - psb + log1y) * b;
+            d2[0] = (psab + a * trab - psa - a * hm_trigamma(a) + logy) * a;
+            d2[1] = (psab + b * trab - psb - b * hm_trigamma(b) + log1y) * b;
+        }
+    }
+    if (logp) logp[row] = lp;
+    for (int i = 0; i < F; ++i) {
+        if (dlogp) dlogp[row * F + i] = d1[i];
+        if (d2logp) d2logp[row * F + i] = d2[i];
+    }
+}
+
+int hm_lik_pointwise(cudaStream_t s, const hmogp_lik_desc& lik, int64_t N, const double* F, const double* Y,
+                     double* logp, double* dlogp, double* d2logp) {
+    if (N <= 0) return 0;
+    const int nf = lik_dimf(lik);
+    lik_pointwise_kernel<<<(unsigned)hm_cdiv(N, HM_LIK_THREADS), HM_LIK_THREADS, 0, s>>>(lik.kind, lik.K, lik.sigma, nf,
+                                                                                        N, F, Y, logp, dlogp, d2logp);
+    HM_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,266 @@
+// fp64 M x M algebra of the HetMOGP hot path: batched GEMM, blocked Cholesky, triangular inverse, K_uu build.
+//
+// Replaces the LAPACK/BLAS calls the reference makes through GPy/scipy:
+//   dpotrf via GPy linalg.jitchol   /root/reference/hetmogp/util.py:198
+//   dpotri via GPy linalg.dpotri    util.py:199, svmogp_inf.py:124
+//   dgemm  via numpy.dot            svmogp_inf.py:120,130-161,236,245-246
+//   RBF.K(Z_q, Z_q)                 util.py:197
+// All matrices are row-major with leading dimension Mp (M padded to 256*2^k with an identity block, so no
+// kernel needs edge handling and the padded block factors/inverts to identity).
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------ GEMM
+// C = alpha * op(A) op(B) + beta * C ; 64x64x16 tiles, 256 threads, 4x4 register tile.  Bounds-checked.
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) dgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A,
+                                                    int lda, int64_t sA, int64_t subA, const double* __restrict__ B,
+                                                    int ldb, int64_t sB, int64_t subB, double beta, double* C, int ldc,
+                                                    int64_t sC, int64_t subC, int nsub, int lower_only) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    if (lower_only && blockIdx.x > blockIdx.y) return;
+    {
+        const int b = blockIdx.z, q = b / nsub, j = b % nsub;
+        A += q * sA + j * subA;
+        B += q * sB + j * subB;
+        C += q * sC + j * subC;
+    }
+    __shared__ double As[BK][BM + 4];
+    __shared__ double Bs[BK][BN + 4];
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int row0 = blockIdx.y * BM, col0 = blockIdx.x * BN;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+    for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+        for (int e = tid; e < BM * BK; e += 256) {
+            int i, k;
+            if (!TA) { i = e / BK; k = e % BK; } else { k = e / BM; i = e % BM; }
+            const int gi = row0 + i, gk = k0 + k;
+            double v = 0.0;
+            if (gi < M && gk < K) v = TA ? A[(int64_t)gk * lda + gi] : A[(int64_t)gi * lda + gk];
+            As[k][i] = v;
+        }
+#pragma unroll
+        for (int e = tid; e < BN * BK; e += 256) {
+            int j, k;
+            if (!TB) { k = e / BN; j = e % BN; } else { j = e / BK; k = e % BK; }
+            const int gj = col0 + j, gk = k0 + k;
+            double v = 0.0;
+            if (gj < N && gk < K) v = TB ? B[(int64_t)gj * ldb + gk] : B[(int64_t)gk * ldb + gj];
+            Bs[k][j] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gi = row0 + ty * 4 + i;
+        if (gi >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gj = col0 + tx * 4 + j;
+            if (gj >= N) continue;
+            double* c = C + (int64_t)gi * ldc + gj;
+            double v = alpha * acc[i][j];
+            if (beta != 0.0) v += beta * (*c);
+            *c = v;
+        }
+    }
+}
+
+int hm_dgemm(cudaStream_t s, bool ta, bool tb, int M, int N, int K, double alpha, const double* A, int lda, int64_t sA,
+             const double* B, int ldb, int64_t sB, double beta, double* C, int ldc, int64_t sC, int batch, int nsub,
+             int64_t subA, int64_t subB, int64_t subC, bool lower_only) {
+    if (M <= 0 || N <= 0 || batch <= 0) return 0;
+    dim3 grid((unsigned)hm_cdiv(N, 64), (unsigned)hm_cdiv(M, 64), (unsigned)(batch * nsub));
+#define HM_LAUNCH_GEMM(TA_, TB_)                                                                                      \
+    dgemm_kernel<TA_, TB_><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, sA, subA, B, ldb, sB, subB, beta, C, ldc, sC, \
+                                                subC, nsub, lower_only ? 1 : 0)
+    if (!ta && !tb) HM_LAUNCH_GEMM(false, false);
+    else if (!ta && tb) HM_LAUNCH_GEMM(false, true);
+    else if (ta && !tb) HM_LAUNCH_GEMM(true, false);
+    else HM_LAUNCH_GEMM(true, true);
+#undef HM_LAUNCH_GEMM
+    HM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------- Cholesky
+// Right-looking blocked lower Cholesky, NB = 32.  Per panel: (1) every CTA factors the 32x32 diagonal block
+// redundantly in shared memory and solves its own 128 rows against it, (2) trailing update by dgemm.
+// A non-positive (or NaN) pivot sets flags[q] and is replaced by 1 so the factorisation runs to the end; the
+// host retries with jitter (GPy jitchol semantics, /root/reference/hetmogp/util.py:198).
+__global__ void __launch_bounds__(128) chol_panel_kernel(double* A, int ld, int64_t sQ, int k0, int n, int* flags) {
+    constexpr int NB = 32;
+    A += blockIdx.y * sQ;
+    __shared__ double D[NB][NB + 1];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < NB * NB; e += 128) {
+        const int i = e / NB, j = e % NB;
+        D[i][j] = A[(int64_t)(k0 + i) * ld + k0 + j];
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const int lane = tid;
+        for (int j = 0; j < NB; ++j) {
+            double sacc = 0.0;
+            if (lane >= j) {
+                sacc = D[lane][j];
+                for (int l = 0; l < j; ++l) sacc -= D[lane][l] * D[j][l];
+            }
+            __syncwarp();
+            if (lane == j) {
+                if (!(sacc > 0.0)) {
+                    if (blockIdx.x == 0) atomicOr(&flags[blockIdx.y], 1);
+                    sacc = 1.0;
+                }
+                D[j][j] = sqrt(sacc);
+            }
+            __syncwarp();
+            if (lane > j) D[lane][j] = sacc / D[j][j];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    const int row = k0 + blockIdx.x * 128 + tid;
+    if (row >= n) return;
+    double* arow = A + (int64_t)row * ld + k0;
+    if (row < k0 + NB) {
+        const int i = row - k0;
+        for (int j = 0; j < NB; ++j) arow[j] = (j <= i) ? D[i][j] : 0.0;
+    } else {
+        double x[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) x[j] = arow[j];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            double sacc = x[j];
+#pragma unroll
+            for (int l = 0; l < j; ++l) sacc -= x[l] * D[j][l];
+            x[j] = sacc / D[j][j];
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) arow[j] = x[j];
+    }
+}
+
+int hm_cholesky(cudaStream_t s, double* A, int Mp, int64_t sQ, int Q, int* flags) {
+    constexpr int NB = 32;
+    for (int k0 = 0; k0 < Mp; k0 += NB) {
+        dim3 grid((unsigned)hm_cdiv(Mp - k0, 128), (unsigned)Q);
+        chol_panel_kernel<<<grid, 128, 0, s>>>(A, Mp, sQ, k0, Mp, flags);
+        HM_CUDA(cudaGetLastError());
+        const int rem = Mp - k0 - NB;
+        if (rem > 0) {
+            const double* P = A + (int64_t)(k0 + NB) * Mp + k0;
+            double* C = A + (int64_t)(k0 + NB) * Mp + k0 + NB;
+            HM_CHECK(hm_dgemm(s, false, true, rem, rem, NB, -1.0, P, Mp, sQ, P, Mp, sQ, 1.0, C, Mp, sQ, Q, 1, 0, 0, 0,
+                              true));
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ triangular inverse
+// X = L^-1 for lower-triangular L: invert the 64x64 diagonal blocks, then merge pairs of inverted blocks of
+// size s = 64, 128, ... with X21 = -X22 (L21 X11) (two batched GEMMs per level).  X must be zero on entry.
+__global__ void __launch_bounds__(64) triinv_diag_kernel(const double* __restrict__ L, double* X, int ld, int64_t sQ) {
+    constexpr int NB = 64;
+    L += blockIdx.y * sQ;
+    X += blockIdx.y * sQ;
+    const int o = blockIdx.x * NB;
+    extern __shared__ double triinv_smem[];
+    double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(triinv_smem);
+    double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(triinv_smem + NB * (NB + 1));
+    for (int e = threadIdx.x; e < NB * NB; e += 64) {
+        const int i = e / NB, j = e % NB;
+        Ls[i][j] = L[(int64_t)(o + i) * ld + o + j];
+    }
+    __syncthreads();
+    const int c = threadIdx.x;
+    for (int i = 0; i < NB; ++i) {
+        double v;
+        if (i < c) v = 0.0;
+        else if (i == c) v = 1.0 / Ls[c][c];
+        else {
+            double sacc = 0.0;
+            for (int l = c; l < i; ++l) sacc += Ls[i][l] * Xs[l][c];
+            v = -sacc / Ls[i][i];
+        }
+        Xs[i][c] = v;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < NB * NB; e += 64) {
+        const int i = e / NB, j = e % NB;
+        X[(int64_t)(o + i) * ld + o + j] = Xs[i][j];
+    }
+}
+
+int hm_tri_inverse(cudaStream_t s, const double* L, double* X, double* tmp, int Mp, int64_t sQ, int Q) {
+    HM_CUDA(cudaMemsetAsync(X, 0, sizeof(double) * sQ * Q, s));
+    dim3 grid((unsigned)(Mp / 64), (unsigned)Q);
+    const int triinv_bytes = 2 * 64 * 65 * (int)sizeof(double);
+    HM_CUDA(cudaFuncSetAttribute(triinv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, triinv_bytes));
+    triinv_diag_kernel<<<grid, 64, triinv_bytes, s>>>(L, X, Mp, sQ);
+    HM_CUDA(cudaGetLastError());
+    for (int sz = 64; sz < Mp; sz *= 2) {
+        const int npairs = Mp / (2 * sz);
+        const int64_t sub = (int64_t)2 * sz * (Mp + 1);
+        const int64_t o21 = (int64_t)sz * Mp;           // block (1,0) of a pair
+        const int64_t o22 = (int64_t)sz * Mp + sz;      // block (1,1)
+        // tmp21 = L21 * X11
+        HM_CHECK(hm_dgemm(s, false, false, sz, sz, sz, 1.0, L + o21, Mp, sQ, X, Mp, sQ, 0.0, tmp + o21, Mp, sQ, Q,
+                          npairs, sub, sub, sub));
+        // X21 = -X22 * tmp21
+        HM_CHECK(hm_dgemm(s, false, false, sz, sz, sz, -1.0, X + o22, Mp, sQ, tmp + o21, Mp, sQ, 0.0, X + o21, Mp, sQ,
+                          Q, npairs, sub, sub, sub));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- K_uu
+// GPy RBF.K(Z_q, Z_q): sigma^2 exp(-r^2/2) with the diagonal of r^2 forced to 0;
+// identity in the padded block; optional jitter on the diagonal (jitchol retry).
+__global__ void build_kuu_kernel(const double* __restrict__ Zp, const HmConsts* __restrict__ c,
+                                 const double* __restrict__ jitter, double* Kuu, int M, int Mp, int Xdim) {
+    const int q = blockIdx.z;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= Mp) return;
+    double v;
+    if (i < M && j < M) {
+        if (i == j) v = c->var[q] + (jitter ? jitter[q] : 0.0);
+        else {
+            const double* zi = Zp + ((int64_t)q * Mp + i) * Xdim;
+            const double* zj = Zp + ((int64_t)q * Mp + j) * Xdim;
+            double r2 = 0.0;
+            for (int k = 0; k < Xdim; ++k) { const double d = zi[k] - zj[k]; r2 += d * d; }
+            v = c->var[q] * exp(-0.5 * r2 * c->inv_l2[q]);
+        }
+    } else v = (i == j) ? 1.0 : 0.0;
+    Kuu[((int64_t)q * Mp + i) * Mp + j] = v;
+}
+
+int hm_build_kuu(cudaStream_t s, const double* Zp, const HmConsts* c, const double* jitter, double* Kuu, int M, int Mp,
+                 int Xdim, int Q) {
+    dim3 grid((unsigned)hm_cdiv(Mp, 128), (unsigned)Mp, (unsigned)Q);
+    build_kuu_kernel<<<grid, 128, 0, s>>>(Zp, c, jitter, Kuu, M, Mp, Xdim);
+    HM_CUDA(cudaGetLastError());
+    return 0;
+}
