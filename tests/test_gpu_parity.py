@@ -1,0 +1,213 @@
+"""GPU (-m gpu): the CUDA engine, called through the C-ABI (ctypes), against
+  (1) the committed golden vectors of the UNMODIFIED reference (tests/golden/), and
+  (2) the CPU oracle (oracle/diag_oracle.py) on seeded inputs,
+plus size-independent properties at larger N.
+
+Tolerances (rel. inf-norm per block unless noted):
+  fp64 mode  ELBO 1e-10, every gradient block 1e-7, per-row m/v/VE/dm/dv 1e-7     (round-off of fp64 M x M algebra)
+  fp32 mode  ELBO 1e-4 (north_star), gradient blocks 5e-3, rows 2e-2              (fp32 tiles, fp64 reductions)
+  integer / index outputs: bit-exact.
+"""
+import numpy as np
+import pytest
+
+import golden_util as gu
+import parity_util as pu
+from oracle import diag_oracle, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp64": dict(elbo=1e-10, grad=1e-7, row=1e-7), "fp32": dict(elbo=1e-4, grad=5e-3, row=2e-2)}
+GRADS = ("dL_dmu_u", "dL_dL_u", "dL_dKmm", "d_rbf", "dW", "dkappa", "dZ")
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("name", gu.CASES)
+def test_engine_matches_reference_golden(name, precision):
+    prob, g = gu.load_case(name)
+    eng = pu.make_engine(prob, precision)
+    out = eng.evaluate(pu.params_of(prob), what="full", want_dKmm=True)
+    tol = TOL[precision]
+    assert abs(out["log_marginal"][0, 0] - g["log_marginal"][0, 0]) <= tol["elbo"] * abs(g["log_marginal"][0, 0])
+    for k in GRADS:
+        assert pu.relerr(out[k], g[k]) < tol["grad"], k
+    # per-function posterior moments of q(f_d) (svmogp_inf.py:216-218)
+    fi, di = g["meta_function_index"], g["meta_d_index"]
+    rows = [eng.rows(t) for t in range(prob["T"])]
+    for d in range(prob["J"]):
+        assert pu.relerr(rows[fi[d]]["m"][:, di[d]], g["m_fd_%d" % d][:, 0]) < tol["row"]
+        assert pu.relerr(rows[fi[d]]["v"][:, di[d]], g["v_fd_%d" % d][:, 0]) < tol["row"]
+    # dense N-sized blocks of the gradients dict (svmogp_inf.py:157-164), small N
+    for q, d in ((0, 0), (prob["Q"] - 1, prob["J"] - 1)):
+        kmn, kdiag = eng.dense_dL_dKmn(q, d)
+        assert pu.relerr(kmn, g["dL_dKmn_%d_%d" % (q, d)]) < tol["grad"]
+        assert pu.relerr(kdiag, g["dL_dKdiag_%d_%d" % (q, d)].ravel()) < tol["row"]
+    eng.close()
+
+
+@pytest.mark.parametrize("tag", gu.LIK_TAGS)
+def test_likelihood_plugins_match_reference_golden(tag):
+    from hetmogp_b200 import likelihoods as L
+    g = gu.load_likelihoods()
+    lik = L.from_spec(gu.LIK_SPECS[tag])
+    Y, M, V = g[tag + "_Y"], g[tag + "_M"], g[tag + "_V"]
+    for prec, tol in (("fp64", 1e-9), ("fp32", 2e-4)):
+        lik.precision = prec
+        ve = lik.var_exp(Y, M, V)
+        dm, dv = lik.var_exp_derivatives(Y, M, V)
+        assert ve.shape == g[tag + "_ve"].shape and dm.shape == g[tag + "_dm"].shape
+        assert pu.relerr(ve, g[tag + "_ve"]) < tol, prec
+        assert pu.relerr(dm, g[tag + "_dm"]) < tol, prec
+        assert pu.relerr(dv, g[tag + "_dv"]) < tol, prec
+    # pointwise methods (fp64)
+    lp = lik.logpdf(M, Y)
+    assert pu.relerr(lp, g[tag + "_logpdf"]) < 1e-10
+    if tag + "_dlogp" in g:
+        F = M.shape[1]
+        if tag.startswith("Categorical"):
+            d1 = np.hstack([lik.dlogp_df(d, M, Y) for d in range(F)])
+            d2 = np.hstack([lik.d2logp_df2(d, M, Y) for d in range(F)])
+        elif tag in ("Gamma", "Beta"):
+            d1, d2 = np.hstack(lik.dlogp_df(M, Y)), np.hstack(lik.d2logp_df2(M, Y))
+        else:
+            d1, d2 = lik.dlogp_df(M, Y), lik.d2logp_df2(M, Y)
+        assert pu.relerr(d1, g[tag + "_dlogp"]) < 1e-9
+        assert pu.relerr(d2, g[tag + "_d2logp"]) < 1e-9
+
+
+def test_index_kernels_bit_exact():
+    """flat_to_triang / triang_to_flat (svmogp_inf.py:118,176-178): pure index maps -> bit-exact."""
+    import ctypes as C
+    from hetmogp_b200 import _lib
+    rng = np.random.default_rng(5)
+    for M, D in ((1, 1), (7, 3), (33, 2), (200, 1)):
+        P = M * (M + 1) // 2
+        flat = rng.normal(size=(P, D))
+        dense = np.full((D, M, M), np.nan)
+        _lib.check(_lib.lib.hmogp_flat_to_triang(flat.ctypes.data, dense.ctypes.data, M, D, 0, None))
+        ii, jj = np.tril_indices(M)
+        ref = np.zeros((D, M, M))
+        for d in range(D):
+            ref[d, ii, jj] = flat[:, d]
+        assert np.array_equal(dense, ref)
+        back = np.empty_like(flat)
+        _lib.check(_lib.lib.hmogp_triang_to_flat(dense.ctypes.data, back.ctypes.data, M, D, 0, None))
+        assert np.array_equal(back, flat)
+
+
+CASES = {
+    "pad_m300": dict(liks=[("Gaussian", 0.5), ("Bernoulli",), ("Poisson",)], N=2500, M=300, Q=3, Xdim=1),
+    "ragged_x2": dict(liks=[("Categorical", 4), ("Gaussian", 0.5)], N=[1500, 1], M=100, Q=2, Xdim=2, kappa_scale=1.0),
+    "m513": dict(liks=[("Bernoulli",)], N=700, M=513, Q=1, Xdim=1),
+}
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_engine_matches_oracle(name, precision):
+    """Padding edges (M not a multiple of the tile, Mp != Mc), ragged tasks (N_t = 1), Xdim = 2."""
+    c = dict(CASES[name])
+    prob = synth.make_problem(c.pop("liks"), c.pop("N"), c.pop("M"), c.pop("Q"), Xdim=c.pop("Xdim"), seed=7, **c)
+    err, out, o = pu.compare(prob, precision)
+    tol = TOL[precision]
+    assert err["elbo"] < tol["elbo"]
+    for k in GRADS:
+        assert err[k] < tol["grad"], (k, err[k])
+    for k, v in err.items():
+        if k.startswith("row_"):
+            assert v < tol["row"], (k, v)
+
+
+def test_what_levels_and_stale_chain():
+    """ELBO-only / VE-step / full agree on shared outputs; W_chain (quirk C-5) follows the oracle."""
+    prob, g = gu.load_case("cfg3_small")
+    eng = pu.make_engine(prob, "fp64")
+    p = pu.params_of(prob)
+    full = eng.evaluate(p, what="full")
+    ve = eng.evaluate(p, what="ve")
+    el = eng.evaluate(p, what="elbo")
+    assert el["log_marginal"][0, 0] == full["log_marginal"][0, 0] == ve["log_marginal"][0, 0]
+    assert np.array_equal(ve["dL_dmu_u"], full["dL_dmu_u"]) and np.array_equal(ve["dL_dL_u"], full["dL_dL_u"])
+    rng = np.random.default_rng(9)
+    prob["W_chain"] = prob["W"] + 0.1 * rng.normal(size=prob["W"].shape)
+    prob["kappa_chain"] = prob["kappa"] + 0.05
+    o = diag_oracle.elbo_and_grads(prob, W_chain=prob["W_chain"], kappa_chain=prob["kappa_chain"])
+    out = eng.evaluate(pu.params_of(prob), what="full")
+    for k in ("d_rbf", "dZ", "dW", "dkappa"):
+        assert pu.relerr(out[k], o[k]) < 1e-8, k
+    eng.close()
+
+
+def test_empty_task_and_row_slices():
+    """Empty tasks contribute nothing; a row slice equals the oracle on the same slice (minibatch / shard)."""
+    prob, g = gu.load_case("cfg2_small")
+    eng = pu.make_engine(prob, "fp64")
+    p = pu.params_of(prob)
+    N = [x.shape[0] for x in prob["X"]]
+    begin, count = [10, 0, 37], [50, 0, N[2] - 37]
+    eng.set_rows(begin, count)
+    out = eng.evaluate(p, what="full")
+    sl = [slice(b, b + c) for b, c in zip(begin, count)]
+    o = diag_oracle.elbo_and_grads(prob, row_slices=sl)
+    assert abs(out["log_marginal"][0, 0] - o["log_marginal"][0, 0]) < 1e-10 * abs(o["log_marginal"][0, 0])
+    assert out["VE"][1] == 0.0
+    for k, ok in (("d_rbf", "d_rbf"), ("dZ", "dZ"), ("dW", "dW")):
+        assert pu.relerr(out[k], o[ok]) < 1e-7
+    eng.close()
+
+
+def test_shard_sum_equals_whole_large_n():
+    """Size-independent property at a large N: the sum of per-shard packed statistics equals the unsharded
+    statistics (the all-reduce identity of the multi-GPU path), and ELBO-from-summed-stats equals the whole."""
+    import ctypes as C
+    import torch
+    from hetmogp_b200 import _lib, shard_rows
+    prob = synth.make_problem([("Gaussian", 0.5), ("Bernoulli",), ("Poisson",)], 60000, 200, 3, seed=21)
+    eng = pu.make_engine(prob, "fp32")
+    p = pu.params_of(prob)
+    whole = eng.evaluate(p, what="full")
+    n = int(_lib.lib.hmogp_stats_len(eng._h))
+    acc = torch.zeros(n, dtype=torch.float64, device="cuda")
+    buf = torch.empty(n, dtype=torch.float64, device="cuda")
+    keep = []
+    ps = eng._params(p, keep)
+    N = [x.shape[0] for x in prob["X"]]
+    for r in range(4):
+        eng.set_rows(*shard_rows(N, r, 4))
+        _lib.check(_lib.lib.hmogp_step_local(eng._h, C.byref(ps), 0, 2, C.c_void_p(buf.data_ptr())))
+        torch.cuda.synchronize()
+        acc += buf
+    out, gs = eng._alloc_out(2, False, True)
+    st = _lib.Status()
+    _lib.check(_lib.lib.hmogp_step_finish(eng._h, C.c_void_p(acc.data_ptr()), C.byref(gs), 0, 2, C.byref(st)))
+    assert abs(out["log_marginal"][0, 0] - whole["log_marginal"][0, 0]) < 1e-9 * abs(whole["log_marginal"][0, 0])
+    for k in GRADS:
+        assert pu.relerr(out[k], whole[k]) < 2e-5, k
+    # and against the oracle on a bounded row sample (oracle cost is linear in N)
+    sub = synth.subsample(prob, 4000)
+    eng2 = pu.make_engine(sub, "fp32")
+    o = diag_oracle.elbo_and_grads(sub)
+    e2 = eng2.evaluate(pu.params_of(sub), what="full")
+    assert abs(e2["log_marginal"][0, 0] - o["log_marginal"][0, 0]) < 1e-4 * abs(o["log_marginal"][0, 0])
+    eng.close()
+    eng2.close()
+
+
+def test_jitter_and_error_conventions():
+    """jitchol semantics (util.py:198): duplicate inducing points -> K_uu singular -> jitter var*1e-6*10^k used;
+    the status reports it; a singular L_u raises ValueError like svmogp_inf.py:126-127."""
+    prob = synth.make_problem([("Gaussian", 0.5)], 300, 16, 1, seed=2)
+    prob["Z"][1] = prob["Z"][0]
+    eng = pu.make_engine(prob, "fp64")
+    out = eng.evaluate(pu.params_of(prob), what="elbo")
+    assert eng.status["jitter"][0] > 0 and np.isfinite(out["log_marginal"][0, 0])
+    o = diag_oracle.elbo_and_grads(prob, want_hyper=False)
+    assert abs(o["jitter"][0] - eng.status["jitter"][0]) <= 1e-12 * o["jitter"][0]
+    assert abs(out["log_marginal"][0, 0] - o["log_marginal"][0, 0]) < 1e-6 * abs(o["log_marginal"][0, 0])
+    prob2 = synth.make_problem([("Gaussian", 0.5)], 300, 16, 1, seed=2)
+    prob2["L_u"][0] = 0.0   # zero pivot -> inf in S^-1
+    eng2 = pu.make_engine(prob2, "fp64")
+    with pytest.raises(ValueError, match="unstable"):
+        eng2.evaluate(pu.params_of(prob2), what="ve")
+    eng.close()
+    eng2.close()
