@@ -93,7 +93,8 @@ def _load():
         "hmogp_flat_to_triang": (C.c_int, [vp, vp, i32, i32, i32, vp]),
         "hmogp_triang_to_flat": (C.c_int, [vp, vp, i32, i32, i32, vp]),
         "hmogp_enable_timing": (C.c_int, [vp, i32]),
-        "hmogp_last_timing": (C.c_int, [vp] + [C.POINTER(C.c_float)] * 5 + [c_int32_p]),
+        "hmogp_last_timing": (C.c_int, [vp, C.POINTER(C.c_float), c_int32_p]),
+        "hmogp_tc_built": (C.c_int, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch

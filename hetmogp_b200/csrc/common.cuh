@@ -14,10 +14,17 @@
 #define HM_MAXXD 4
 
 void hm_set_error(const char* fmt, ...);
+// Every kernel launch in this library is followed by HM_CUDA(cudaGetLastError()); that convention doubles as the
+// launch counter reported to bench.py (gpu_launches).
+extern long long hm_launch_counter;
+static inline void hm_note_call(const char* text) {
+    if (text[0] == 'c' && text[4] == 'G' && text[7] == 'L' && text[11] == 'E') ++hm_launch_counter;  // "cudaGetLastError()"
+}
 
 #define HM_CUDA(call)                                                                          \
     do {                                                                                       \
         cudaError_t _e = (call);                                                               \
+        hm_note_call(#call);                                                                   \
         if (_e != cudaSuccess) {                                                               \
             hm_set_error("%s:%d CUDA error: %s (%s)", __FILE__, __LINE__, cudaGetErrorString(_e), #call); \
             return HMOGP_ERR_CUDA;                                                             \

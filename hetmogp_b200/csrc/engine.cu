@@ -19,6 +19,7 @@
 
 // ------------------------------------------------------------------------------------------ error text
 static thread_local char g_err[512] = "";
+long long hm_launch_counter = 0;
 void hm_set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -374,9 +375,9 @@ struct hmogp_engine {
     int last_what;
     // timing
     bool timing;
-    cudaEvent_t ev[6];
-    float ms[5];
-    int launches;
+    cudaEvent_t ev[7];
+    float ms[6];
+    long long launches, launch0;
     std::vector<void*> allocs;
 };
 
@@ -402,7 +403,7 @@ int lik_dims(const hmogp_lik_desc& l, int* dy, int* df, int* dp) {
             *dy = 1; *df = 2; *dp = 1; return 0;
         case HMOGP_LIK_CATEGORICAL:
             if (l.K < 2 || l.K - 1 > HM_MAXF) { hm_set_error("Categorical K=%d unsupported (2..%d)", l.K, HM_MAXF + 1); return HMOGP_ERR_ARG; }
-            *dy = 1; *df = l.K - 1; *dp = l.K; return 0;
+            *dy = 1; *df = l.K - 1; *dp = l.K - 1; return 0;  // categorical.py:287-291
         default: hm_set_error("unknown likelihood kind %d", l.kind); return HMOGP_ERR_ARG;
     }
 }
@@ -630,7 +631,7 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
 #undef A_
     if (!rc && hm_upload_gh_tables()) rc = HMOGP_ERR_CUDA;
     if (!rc) {
-        for (int i = 0; i < 6; ++i)
+        for (int i = 0; i < 7; ++i)
             if (cudaEventCreate(&e->ev[i]) != cudaSuccess) { hm_set_error("cudaEventCreate failed"); rc = HMOGP_ERR_CUDA; break; }
     }
     if (rc) { hmogp_destroy(e); return rc; }
@@ -648,7 +649,7 @@ void hmogp_destroy(hmogp_engine* e) {
         if (e->tk.AC[t]) cudaFree(e->tk.AC[t]);
         if (e->tk.MW[t]) cudaFree(e->tk.MW[t]);
     }
-    for (int i = 0; i < 6; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    for (int i = 0; i < 7; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     delete e;
 }
 
@@ -708,7 +709,7 @@ int hmogp_step_local(hmogp_engine* e, const hmogp_params* p, int32_t mem_kind, i
     cudaStream_t s = e->stream;
     double* stats = stats_dev ? stats_dev : e->stats;
     e->last_what = what;
-    e->launches = 0;
+    e->launch0 = hm_launch_counter;
     if (e->timing) HM_CUDA(cudaEventRecord(e->ev[0], s));
     HM_CHECK(mm_prepare(e, p, mem_kind));
     if (e->timing) HM_CUDA(cudaEventRecord(e->ev[1], s));
@@ -717,7 +718,6 @@ int hmogp_step_local(hmogp_engine* e, const hmogp_params* p, int32_t mem_kind, i
     // ---- forward projections
     if (e->prec == HMOGP_PREC_TC) HM_CHECK(hm_tc_proj_fwd(s, e->tk, pa, e->Cb));
     else HM_CHECK(hm_proj_fwd(s, e->prec, e->tk, pa));
-    e->launches += 1;
     if (e->timing) HM_CUDA(cudaEventRecord(e->ev[2], s));
     // ---- likelihoods
     const int simt_prec = (e->prec == HMOGP_PREC_FP64) ? HMOGP_PREC_FP64 : HMOGP_PREC_FP32;
@@ -729,7 +729,6 @@ int hmogp_step_local(hmogp_engine* e, const hmogp_params* p, int32_t mem_kind, i
         reduce_lik_kernel<<<1, 128, 0, s>>>(e->lik_part, nb, nstat, stats, t, e->T, e->J, e->Q, e->tk.foff[t], e->tk.dimf[t],
                                             e->off_sdv, e->off_sma, e->off_svc);
         HM_CUDA(cudaGetLastError());
-        e->launches += 2;
     }
     if (e->timing) HM_CUDA(cudaEventRecord(e->ev[3], s));
     // ---- backward statistics
@@ -740,13 +739,13 @@ int hmogp_step_local(hmogp_engine* e, const hmogp_params* p, int32_t mem_kind, i
         reduce_col_kernel<<<g1, 256, 0, s>>>(e->colpart, e->nworkers, ncol, e->Mc, e->Mp, e->Xd, stats + e->off_g1,
                                              stats + e->off_dz, stats + e->off_dls);
         HM_CUDA(cudaGetLastError());
+        if (e->timing) HM_CUDA(cudaEventRecord(e->ev[4], s));
         HM_CHECK(hm_gram(s, simt_prec, e->tk, pa, e->Hpart, e->nsplit));
         dim3 g2((unsigned)hm_cdiv(e->Mp, 128), (unsigned)e->Mp, (unsigned)e->Q);
         reduce_gram_kernel<<<g2, 128, 0, s>>>(e->Hpart, e->nsplit, e->Q, e->Mc, e->Mp, hm_gram_tile(simt_prec), stats + e->off_H);
         HM_CUDA(cudaGetLastError());
-        e->launches += 4;
-    }
-    if (e->timing) HM_CUDA(cudaEventRecord(e->ev[4], s));
+    } else if (e->timing) HM_CUDA(cudaEventRecord(e->ev[4], s));
+    if (e->timing) HM_CUDA(cudaEventRecord(e->ev[5], s));
     return 0;
 }
 
@@ -799,7 +798,7 @@ int hmogp_step_finish(hmogp_engine* e, const double* stats_dev, hmogp_grads* g, 
         assemble_mat_kernel<<<gm, 128, 0, s>>>(a);
         HM_CUDA(cudaGetLastError());
     }
-    if (e->timing) HM_CUDA(cudaEventRecord(e->ev[5], s));
+    if (e->timing) HM_CUDA(cudaEventRecord(e->ev[6], s));
     // ---- outputs
     const size_t P = e->P;
     HM_CHECK(copy_out(e, g->log_marginal, e->o_lm, 1, mem_kind));
@@ -822,10 +821,11 @@ int hmogp_step_finish(hmogp_engine* e, const double* stats_dev, hmogp_grads* g, 
     HM_CUDA(cudaMemcpyAsync(nneg, stats + e->off_nneg, sizeof(double) * e->T, cudaMemcpyDeviceToHost, s));
     HM_CUDA(cudaStreamSynchronize(s));
     if (e->timing) {
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < 6; ++i) {
             if (cudaEventElapsedTime(&e->ms[i], e->ev[i], e->ev[i + 1]) != cudaSuccess) e->ms[i] = -1.f;
         }
     }
+    e->launches = hm_launch_counter - e->launch0;
     bool unstable = false;
     if (status) {
         memset(status, 0, sizeof(*status));
@@ -1045,16 +1045,13 @@ int hmogp_enable_timing(hmogp_engine* e, int32_t on) {
     return 0;
 }
 
-int hmogp_last_timing(hmogp_engine* e, float* ms_prepare, float* ms_forward, float* ms_lik, float* ms_backward,
-                      float* ms_finish, int32_t* launches) {
+int hmogp_last_timing(hmogp_engine* e, float* ms, int32_t* launches) {
     if (!e) { hm_set_error("null engine"); return HMOGP_ERR_ARG; }
-    if (ms_prepare) *ms_prepare = e->ms[0];
-    if (ms_forward) *ms_forward = e->ms[1];
-    if (ms_lik) *ms_lik = e->ms[2];
-    if (ms_backward) *ms_backward = e->ms[3];
-    if (ms_finish) *ms_finish = e->ms[4];
-    if (launches) *launches = e->launches;
+    if (ms) for (int i = 0; i < 6; ++i) ms[i] = e->ms[i];
+    if (launches) *launches = (int32_t)e->launches;
     return 0;
 }
+
+int hmogp_tc_built(void) { return hm_tc_available(); }
 
 }  // extern "C"

@@ -187,11 +187,13 @@ class Engine(object):
         check(lib.hmogp_enable_timing(self._h, 1 if on else 0))
 
     def last_timing(self):
-        f = [C.c_float() for _ in range(5)]
+        f = (C.c_float * 6)()
         n = C.c_int32()
-        check(lib.hmogp_last_timing(self._h, *[C.byref(x) for x in f], C.byref(n)))
-        return {"prepare_ms": f[0].value, "forward_ms": f[1].value, "lik_ms": f[2].value, "backward_ms": f[3].value,
-                "finish_ms": f[4].value, "launches": n.value}
+        check(lib.hmogp_last_timing(self._h, f, C.byref(n)))
+        names = ("prepare_ms", "forward_ms", "lik_ms", "bwd_proj_ms", "bwd_gram_ms", "finish_ms")
+        d = {k: float(f[i]) for i, k in enumerate(names)}
+        d["launches"] = n.value
+        return d
 
 
 def shard_rows(N, rank, world):

@@ -180,8 +180,10 @@ int hmogp_triang_to_flat(const double* dense, double* flat, int32_t M, int32_t D
 /* ---- timing hooks for bench.py: CUDA-event time (ms) and launch count of the N-sized kernels of the
  *      last evaluation, measured on the engine's stream. ---- */
 int hmogp_enable_timing(hmogp_engine* e, int32_t on);
-int hmogp_last_timing(hmogp_engine* e, float* ms_prepare, float* ms_forward, float* ms_lik, float* ms_backward,
-                      float* ms_finish, int32_t* launches);
+int hmogp_last_timing(hmogp_engine* e, float* ms /* [6]: prepare, forward, lik, bwd_proj, bwd_gram, finish */,
+                      int32_t* launches);
+/* 1 if the tcgen05 tensor-core path (HMOGP_PREC_TC) is compiled into this library */
+int hmogp_tc_built(void);
 
 #ifdef __cplusplus
 }

@@ -197,7 +197,7 @@ class Categorical(object):
 
     def __init__(self, K):
         self.K = K
-        self.dims = (1, K - 1, K)
+        self.dims = (1, K - 1, K - 1)   # categorical.py:287-291
 
     def get_metadata(self):
         return self.dims
