@@ -47,10 +47,8 @@ struct HmLikRowArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(HM_LIK_THREADS) lik_rows_kernel(HmLikRowArgs p) {
-    __shared__ double sacc[HM_LIK_MAXSTAT];
+    __shared__ double sacc[HM_LIK_THREADS / 32][HM_LIK_MAXSTAT];
     const int nstat = 2 + p.dimf * (1 + 2 * p.Q);
-    for (int i = threadIdx.x; i < nstat; i += blockDim.x) sacc[i] = 0.0;
-    __syncthreads();
     const HmConsts* __restrict__ cs = p.consts;
     const int Q = p.Q, F = p.dimf;
     const T bs = T(cs->bscale[p.t]);
@@ -119,15 +117,19 @@ __global__ void __launch_bounds__(HM_LIK_THREADS) lik_rows_kernel(HmLikRowArgs p
             p.rows_ve[row] = (double)o.ve;
         }
     }
-    // block reduction: warp shuffles then one shared-memory atomic per warp and statistic
+    // block reduction in a fixed order (deterministic): warp shuffles, then per-warp slots summed by one thread
     for (int i = 0; i < nstat; ++i) {
         double x = st[i];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[i], x);
+        if ((threadIdx.x & 31) == 0) sacc[threadIdx.x >> 5][i] = x;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nstat; i += blockDim.x) p.partials[(int64_t)blockIdx.x * nstat + i] = sacc[i];
+    for (int i = threadIdx.x; i < nstat; i += blockDim.x) {
+        double x = 0.0;
+        for (int w = 0; w < HM_LIK_THREADS / 32; ++w) x += sacc[w][i];
+        p.partials[(int64_t)blockIdx.x * nstat + i] = x;
+    }
 }
 
 int hm_lik_rows(cudaStream_t s, int prec, const HmTasks& tk, const HmConsts* consts, int t, bool want_grads,

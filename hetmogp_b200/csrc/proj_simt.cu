@@ -134,7 +134,15 @@ __global__ void __launch_bounds__(kThreads, 1) proj_kernel(HmTasks tk, HmProjArg
                 Ks[(size_t)m * BM + r] = kv;
                 apart += kv * als[m];
             }
-            if (!BWD) atomicAdd(&racc[r], (double)apart);
+            if (!BWD) {  // deterministic reduction of the per-thread partials (scratch: the idle C_q stage buffer)
+                Bs[tid] = apart;
+                __syncthreads();
+                if (tid < BM) {
+                    double sacc = 0.0;
+                    for (int g = 0; g < kThreads / BM; ++g) sacc += (double)Bs[g * BM + tid];
+                    racc[tid] = sacc;
+                }
+            }
         }
         __syncthreads();
 
@@ -196,28 +204,36 @@ __global__ void __launch_bounds__(kThreads, 1) proj_kernel(HmTasks tk, HmProjArg
                         if (lane == 0) racc[BM + w * TM + i] += (double)cp;
                     }
                 } else {
+                    // column sums over the tile rows: per-warp partials -> fixed-order cross-warp sum through shared
+                    // memory (scratch: the idle C_q stage buffer) -> single owner per column: deterministic
+                    double* red = reinterpret_cast<double*>(Bs);   // [8 warps][256 columns]
+                    for (int i2 = 0; i2 < Xd; ++i2) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int col = jb + (j < 4 ? lane * 4 + j : 128 + lane * 4 + (j - 4));
-                        const T al = als[col];
-                        double dzs[HM_MAXXD];
-                        for (int i2 = 0; i2 < HM_MAXXD; ++i2) dzs[i2] = 0.0;
-                        T dl = T(0);
+                        for (int j = 0; j < 8; ++j) {
+                            const int slot = (j < 4 ? lane * 4 + j : 128 + lane * 4 + (j - 4));
+                            const int col = jb + slot;
+                            const T al = als[col];
+                            T pz = T(0), dl = T(0);
 #pragma unroll
-                        for (int i = 0; i < TM; ++i) {
-                            const int r = w * TM + i;
-                            const T kv = Ks[(size_t)col * BM + r];
-                            const T gk = kv * (rw[2 * BM + r] * al + T(2) * rw[3 * BM + r] * acc[i][j]);
-                            T d2 = T(0);
-                            for (int i2 = 0; i2 < Xd; ++i2) {
+                            for (int i = 0; i < TM; ++i) {
+                                const int r = w * TM + i;
+                                const T kv = Ks[(size_t)col * BM + r];
+                                const T gk = kv * (rw[2 * BM + r] * al + T(2) * rw[3 * BM + r] * acc[i][j]);
                                 const T d = (xh[r * Xd + i2] - zh[col * Xd + i2]) + (xl[r * Xd + i2] - zl[col * Xd + i2]);
-                                d2 += d * d;
-                                dzs[i2] += (double)(gk * d);
+                                pz += gk * d;
+                                dl += gk * d * d;
                             }
-                            dl += gk * d2;
+                            dls_thread += (double)dl;   // sum over input dims of GK d_i^2 = GK |x - z|^2
+                            red[w * kBN + slot] = (double)pz;
                         }
-                        dls_thread += (double)dl;
-                        for (int i2 = 0; i2 < Xd; ++i2) atomicAdd(&colacc[(1 + i2) * Mc + col], dzs[i2]);
+                        __syncthreads();
+                        {
+                            double sacc = 0.0;
+#pragma unroll
+                            for (int ww = 0; ww < kThreads / 32; ++ww) sacc += red[ww * kBN + tid];
+                            colacc[(1 + i2) * Mc + jb + tid] += sacc;
+                        }
+                        __syncthreads();
                     }
                 }
             }
@@ -242,10 +258,15 @@ __global__ void __launch_bounds__(kThreads, 1) proj_kernel(HmTasks tk, HmProjArg
         __syncthreads();
     }
     if (BWD) {
-        // dls: block reduce
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) dls_thread += __shfl_xor_sync(0xffffffffu, dls_thread, off);
-        if (lane == 0) atomicAdd(&colacc[ncol - 1], dls_thread);
+        // dls: fixed-order block reduce
+        double* red = reinterpret_cast<double*>(Bs);
+        red[tid] = dls_thread;
+        __syncthreads();
+        if (tid == 0) {
+            double sacc = 0.0;
+            for (int i = 0; i < kThreads; ++i) sacc += red[i];
+            colacc[ncol - 1] = sacc;
+        }
         __syncthreads();
         double* out = pa.colpart + ((size_t)q * gridDim.x + blockIdx.x) * ncol;
         for (int i = tid; i < ncol; i += kThreads) out[i] = colacc[i];
