@@ -61,8 +61,16 @@ struct HmTasks {
     const double* Y[HM_MAXT];  // [N_t]
     int64_t begin[HM_MAXT];    // active slice
     int64_t count[HM_MAXT];
-    void* AC[HM_MAXT];         // [count, 2Q]  a_tq, c_tq          (compute type)
+    void* AC[HM_MAXT];         // [count, acs] a_tq, c_tq (+ b_tq, e_tq on the tensor-core path)  (compute type)
     void* MW[HM_MAXT];         // [count, 4Q]  mu, omega, mu_c, omega_c (compute type)
+    int acs;                   // AC row stride in elements: 2Q (SIMT) or 4Q (tensor-core path)
+};
+
+// Per-step scale state of the tensor-core path (device resident; see tc_common.cuh "split fp16").
+struct HmTcInfo {
+    int cexp[HM_MAXQ];             // C_q is carried as C_q * 2^cexp   (|.| < 2^14)
+    int kexp[HM_MAXQ];             // K_tq is carried as K_tq * 2^kexp (sigma_q^2 -> [2^11, 2^12))
+    unsigned wmax[2][HM_MAXQ];     // float bits of max_n |omega_tq|, max_n |omega^c_tq| (likelihood kernel, atomicMax)
 };
 
 // ---------------------------------------------------------------- M x M fp64 algebra (mm_algebra.cu)
@@ -81,7 +89,7 @@ struct HmLikStatsLayout {
 };
 int hm_lik_rows(cudaStream_t s, int prec, const HmTasks& tk, const HmConsts* consts, int t, bool want_grads,
                 bool has_chain, double* partials, int max_blocks, int* nblocks_out, double* rows_m, double* rows_v,
-                double* rows_ve, double* rows_dm, double* rows_dv);
+                double* rows_ve, double* rows_dm, double* rows_dv, HmTcInfo* tcinfo = nullptr, bool hyper = false);
 int hm_lik_var_exp(cudaStream_t s, int prec, const hmogp_lik_desc& lik, int64_t N, const double* Y, const double* Mf,
                    const double* Vf, double* VE, double* dm, double* dv);
 int hm_lik_pointwise(cudaStream_t s, const hmogp_lik_desc& lik, int64_t N, const double* F, const double* Y,
@@ -103,3 +111,24 @@ int hm_proj_bwd(cudaStream_t s, int prec, const HmTasks& tk, const HmProjArgs& a
 int hm_proj_workers(int prec, int Mc);
 int hm_gram(cudaStream_t s, int prec, const HmTasks& tk, const HmProjArgs& a, double* Hpart, int nsplit);
 int hm_gram_splits(int prec, int Mc, int Q);
+int hm_gram_tile(int prec);
+
+// ---------------------------------------------------------------- tensor-core path (tc_fwd.cu, tc_gram.cu)
+#define HM_GRAM_CHUNK 32                                   // data rows per Gram stage
+#define HM_GRAM_MAXV 6                                     // g-vectors per launch
+#define HM_GRAM_SLOT_DOUBLES (2 * 128 * 256 + HM_GRAM_MAXV * 128)
+struct HmGramJob { int I, j0, nw; };                       // output tile: rows [128 I, 128 I + 128), columns [j0, j0 + nw)
+struct HmGramSeg { int q, I, j0, nw, chunk_begin, chunk_end, slot, has_g; };
+struct HmGramWeights {                                     // what one Gram launch accumulates
+    int nW, wbase[2], wdim[2];                             // H^k: weight = MW[wbase] (1 omega | 3 omega^c) * (wdim >= 0 ? s (x - z_row)[wdim] : 1)
+    int nV, vbase[HM_GRAM_MAXV], vdim[HM_GRAM_MAXV];       // g^v: weight = MW[vbase] (0 mu | 2 mu^c) * (vdim >= 0 ? s (x - z_row)[vdim] : 1)
+};
+int hm_tc_available();
+size_t hm_tc_image_elems(int Mc, int Q);
+int hm_tc_prepare(cudaStream_t s, const double* C, const HmConsts* consts, HmTcInfo* info, void* Cb, int M, int Mp, int Mc, int Q);
+int hm_tc_proj_fwd(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const void* Cb, const HmTcInfo* info, bool hyper,
+                   int npass);
+int hm_tc_gram(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const HmTcInfo* info, const HmGramSeg* segs,
+               const int* seg_off, const HmGramWeights& gw, double* slots, int nctas, int flush_chunks, int npass);
+int hm_tc_gram_reduce(cudaStream_t s, const double* slots, const HmGramJob* jobs, const int2* jobslots, int njobs, int Q,
+                      const HmGramWeights& gw, double* H0, double* H1, double* g0, int64_t gstride, int M, int Mp);

@@ -27,11 +27,7 @@ void hm_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-int hm_gram_tile(int prec);
-// tensor-core path (proj_tc.cu)
-int hm_tc_available();
-int hm_tc_prepare(cudaStream_t s, const double* C, const double* alpha, void* Cb, int Mp, int Mc, int Q);
-int hm_tc_proj_fwd(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const void* Cb);
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------ small kernels
 namespace {
@@ -133,13 +129,15 @@ __global__ void kl_kernel(const double* Ki, const double* S, const double* Sinv,
 
 // ---- statistic reducers (deterministic: fixed summation order)
 __global__ void reduce_lik_kernel(const double* partials, int nblocks, int nstat, double* stats, int t, int T, int J, int Q,
-                                  int foff, int dimf, int off_sdv, int off_sma, int off_svc) {
+                                  int foff, int dimf, int off_sdv, int off_sma, int off_svc, int off_dls) {
     const int i = threadIdx.x;
     if (i >= nstat) return;
     double s = 0.0;
     for (int b = 0; b < nblocks; ++b) s += partials[(int64_t)b * nstat + i];
+    const int nbase = 2 + dimf * (1 + 2 * Q);
     if (i == 0) stats[t] = s;
     else if (i == 1) stats[T + t] = s;
+    else if (i >= nbase) stats[off_dls + (i - nbase)] += s;   // tensor-core path: K_mn lengthscale statistic (tasks run in stream order)
     else {
         const int k = i - 2, f = k / (1 + 2 * Q), r = k % (1 + 2 * Q), d = foff + f;
         if (r == 0) stats[off_sdv + d] = s;
@@ -338,6 +336,38 @@ __global__ void extract_mm_kernel(const double* src, double* dst, int M, int Mp,
     dst[((int64_t)q * M + i) * M + j] = (lower_only && j > i) ? 0.0 : src[((int64_t)q * Mp + i) * Mp + j];
 }
 
+// Inducing-input statistic of the K_mn chain from the distance-weighted Grams (tensor-core path):
+//   dz[q][i][m] = sum_n GK[n,m] (x_ni - z_mi) = (1/s) [ alpha_m g^{d_i}_m + 2 sum_j C[m,j] D^i[m,j] ]
+// with D^i[m,j] = sum_n omega^c s (x_ni - z_mi) K[n,m] K[n,j] stored for j <= m and, for j > m,
+//   D^i[m,j] = D^i[j,m] + s (z_ji - z_mi) H^1[j,m]
+// (reference: RBF.gradients_X(dL_dKmn, Z, X), svmogp.py:153-156).  One warp per (q, m).
+__global__ void gram_dz_kernel(const double* __restrict__ C, const double* __restrict__ alpha, const double* __restrict__ Zp,
+                               const HmConsts* __restrict__ cs, const double* __restrict__ H1, const double* __restrict__ Dx,
+                               int64_t hstride, const double* __restrict__ gd, int64_t gstride, double* dz, int M, int Mp,
+                               int Xd) {
+    const int q = blockIdx.y;
+    const int m = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+    if (m >= M) return;
+    const double sscale = sqrt(0.5 * 1.4426950408889634 * cs->inv_l2[q]);
+    const size_t qoff = (size_t)q * Mp * Mp, rowoff = qoff + (size_t)m * Mp;
+    for (int i = 0; i < Xd; ++i) {
+        const double zm = Zp[((size_t)q * Mp + m) * Xd + i];
+        const double* D = Dx + (size_t)i * hstride;
+        double s = 0.0;
+        for (int j = lane; j < M; j += 32) {
+            double dmj;
+            if (j <= m) dmj = D[rowoff + j];
+            else dmj = D[qoff + (size_t)j * Mp + m] + sscale * (Zp[((size_t)q * Mp + j) * Xd + i] - zm) * H1[qoff + (size_t)j * Mp + m];
+            s += C[rowoff + j] * dmj;
+        }
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) {
+            const size_t vi = (size_t)q * Mp + m;
+            dz[((size_t)q * Xd + i) * Mp + m] = (alpha[vi] * gd[(size_t)i * gstride + vi] + 2.0 * s) / sscale;
+        }
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ engine state
@@ -357,7 +387,18 @@ struct hmogp_engine {
     double *Zp, *mp, *alpha, *kg;  // [Q][Mp][Xd], [Q][Mp]
     double *Kuu, *Luu, *LuuInv, *Ki, *Lu, *LuInv, *Sinv, *S, *SK, *KSK, *C, *tmp, *T1, *E, *tmpE, *dLdS, *dLdLfull, *dLdK;
     float* Cf;
-    void* Cb;  // tensor-core operand copy of C
+    // tensor-core path
+    void* Cb;              // split-fp16 SW128 operand image of C
+    HmTcInfo* tcinfo;
+    int tc_npass, tc_flush;
+    std::vector<HmGramJob> jobs_h;
+    HmGramJob* jobs_d;
+    HmGramSeg* segs_d; int* segoff_d; int2* jobslots_d;
+    int max_segs, nslots_max;
+    double* slots;         // [nslots][HM_GRAM_SLOT_DOUBLES] fp64 partial tiles
+    double* Hx;            // [1 + Xd][Q][Mp][Mp] extra Grams
+    double* gvec;          // [HM_GRAM_MAXV][Q][Mp]
+    bool plan_dirty;
     double *KLq, *jitter_d, *rowstat, *dzmm;
     int *flags_d;  // [2][HM_MAXQ]: chol_fail, lu_singular
     // statistics
@@ -500,7 +541,7 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
     }
     kl_kernel<<<Q, 1024, 0, s>>>(e->Ki, e->S, e->Sinv, e->mp, e->alpha, e->Luu, e->Lu, e->KLq, e->flags_d + HM_MAXQ, M, Mp);
     HM_CUDA(cudaGetLastError());
-    if (e->prec == HMOGP_PREC_TC) HM_CHECK(hm_tc_prepare(s, e->C, e->alpha, e->Cb, Mp, e->Mc, Q));
+    if (e->prec == HMOGP_PREC_TC) HM_CHECK(hm_tc_prepare(s, e->C, e->consts, e->tcinfo, e->Cb, M, Mp, e->Mc, Q));
     return 0;
 }
 
@@ -509,6 +550,112 @@ int refresh_tasks(hmogp_engine* e) {
         if (!e->Xd_[t]) { hm_set_error("task %d has no data (call hmogp_set_data)", t); return HMOGP_ERR_ARG; }
         e->tk.X[t] = e->Xd_[t];
         e->tk.Y[t] = e->Yd_[t];
+    }
+    return 0;
+}
+
+// ---- tensor-core backward: plan, launches, reduction
+// The work of all (latent q, output tile) pairs is laid on one tape (position = cost-weighted chunk index) and cut into
+// nworkers equal pieces; a piece that crosses a pair boundary becomes several segments, each with a private fp64 partial
+// tile ("slot").  Slots of one pair are contiguous, so the reduction order is fixed.
+int build_gram_plan(hmogp_engine* e) {
+    if (!e->plan_dirty) return 0;
+    const int G = e->nworkers, Q = e->Q, nj = (int)e->jobs_h.size();
+    int64_t NC = 0;
+    for (int t = 0; t < e->T; ++t) NC += hm_cdiv(e->tk.count[t], HM_GRAM_CHUNK);
+    std::vector<HmGramSeg> segs;
+    std::vector<std::vector<HmGramSeg>> per(G);
+    std::vector<int2> jobslots((size_t)Q * nj);
+    std::vector<int64_t> cost(nj);
+    int64_t per_q = 0;
+    for (int j = 0; j < nj; ++j) { cost[j] = e->jobs_h[j].nw + 96; per_q += cost[j]; }
+    const double total = (double)per_q * (double)NC * Q;
+    int slot = 0;
+    double bs = 0.0;   // tape position of the current block
+    for (int q = 0; q < Q; ++q)
+        for (int j = 0; j < nj; ++j) {
+            const double len = (double)cost[j] * (double)NC;
+            jobslots[(size_t)q * nj + j].x = slot;
+            if (NC > 0) {
+                int g0 = (int)((bs / total) * G), g1 = (int)(((bs + len) / total) * G);
+                g0 = g0 > 0 ? g0 - 1 : 0;          // one CTA of slack either side: rounding of the tape positions
+                g1 = g1 + 1;
+                if (g0 > G - 1) g0 = G - 1;
+                if (g1 > G - 1) g1 = G - 1;
+                for (int g = g0; g <= g1; ++g) {
+                    const double ps = total * g / G, pe = (g == G - 1) ? total * 2.0 : total * (g + 1) / G;
+                    int64_t cb = ps <= bs ? 0 : (int64_t)((ps - bs) / (double)cost[j]);
+                    int64_t ce = pe >= bs + len ? NC : (int64_t)((pe - bs) / (double)cost[j]);
+                    if (cb > NC) cb = NC;
+                    if (ce > NC) ce = NC;
+                    if (ce <= cb) continue;
+                    HmGramSeg sg;
+                    sg.q = q; sg.I = e->jobs_h[j].I; sg.j0 = e->jobs_h[j].j0; sg.nw = e->jobs_h[j].nw;
+                    sg.chunk_begin = (int)cb; sg.chunk_end = (int)ce; sg.slot = slot++; sg.has_g = (sg.j0 == 0) ? 1 : 0;
+                    per[g].push_back(sg);
+                }
+            }
+            jobslots[(size_t)q * nj + j].y = slot;
+            bs += len;
+        }
+    std::vector<int> off(G + 1, 0);
+    for (int g = 0; g < G; ++g) {
+        off[g] = (int)segs.size();
+        segs.insert(segs.end(), per[g].begin(), per[g].end());
+    }
+    off[G] = (int)segs.size();
+    if ((int)segs.size() > e->max_segs || slot > e->nslots_max) {
+        hm_set_error("gram plan overflow: %d segments, %d slots", (int)segs.size(), slot);
+        return HMOGP_ERR_ARG;
+    }
+    cudaStream_t s = e->stream;
+    HM_CUDA(cudaStreamSynchronize(s));
+    if (!segs.empty()) HM_CUDA(cudaMemcpy(e->segs_d, segs.data(), sizeof(HmGramSeg) * segs.size(), cudaMemcpyHostToDevice));
+    HM_CUDA(cudaMemcpy(e->segoff_d, off.data(), sizeof(int) * (G + 1), cudaMemcpyHostToDevice));
+    HM_CUDA(cudaMemcpy(e->jobslots_d, jobslots.data(), sizeof(int2) * jobslots.size(), cudaMemcpyHostToDevice));
+    e->plan_dirty = false;
+    return 0;
+}
+
+int tc_backward(hmogp_engine* e, int what, double* stats) {
+    cudaStream_t s = e->stream;
+    const int Q = e->Q, Xd = e->Xd, Mp = e->Mp, M = e->M;
+    const int64_t MM = (int64_t)Q * Mp * Mp, gstride = (int64_t)Q * Mp;
+    HM_CHECK(build_gram_plan(e));
+    HmProjArgs pa = proj_args(e);
+    const bool full = what >= HMOGP_WHAT_FULL, chain = e->has_chain;
+    // weight list: index 0 -> H (E statistic); the rest -> Hx scratch in order
+    int wb[2 + HM_MAXXD], wd[2 + HM_MAXXD], nWt = 0;
+    wb[nWt] = 1; wd[nWt++] = -1;
+    if (full) {
+        if (chain) { wb[nWt] = 3; wd[nWt++] = -1; }
+        for (int i = 0; i < Xd; ++i) { wb[nWt] = chain ? 3 : 1; wd[nWt++] = i; }
+    }
+    HM_CUDA(cudaMemsetAsync(stats + e->off_H, 0, sizeof(double) * MM, s));
+    if (nWt > 1) HM_CUDA(cudaMemsetAsync(e->Hx, 0, sizeof(double) * MM * (nWt - 1), s));
+    for (int w0 = 0; w0 < nWt; w0 += 2) {
+        HmGramWeights gw;
+        memset(&gw, 0, sizeof(gw));
+        gw.nW = (nWt - w0) >= 2 ? 2 : 1;
+        for (int k = 0; k < gw.nW; ++k) { gw.wbase[k] = wb[w0 + k]; gw.wdim[k] = wd[w0 + k]; }
+        if (w0 == 0) {
+            gw.vbase[gw.nV] = 0; gw.vdim[gw.nV++] = -1;                       // g^mu -> dVE/dm
+            if (full)
+                for (int i = 0; i < Xd; ++i) { gw.vbase[gw.nV] = chain ? 2 : 0; gw.vdim[gw.nV++] = i; }   // sum_n mu^c s d_i K
+        }
+        HM_CHECK(hm_tc_gram(s, e->tk, pa, e->tcinfo, e->segs_d, e->segoff_d, gw, e->slots, e->nworkers, e->tc_flush, e->tc_npass));
+        double* H0 = (w0 == 0) ? stats + e->off_H : e->Hx + (int64_t)(w0 - 1) * MM;
+        double* H1 = e->Hx + (int64_t)w0 * MM;
+        HM_CHECK(hm_tc_gram_reduce(s, e->slots, e->jobs_d, e->jobslots_d, (int)e->jobs_h.size(), Q, gw, H0, H1, e->gvec, gstride, M, Mp));
+    }
+    HM_CUDA(cudaMemcpyAsync(stats + e->off_g1, e->gvec, sizeof(double) * gstride, cudaMemcpyDeviceToDevice, s));
+    if (full) {
+        const double* Hc1 = chain ? e->Hx : stats + e->off_H;         // Gram weighted by omega^c
+        const double* Dx = chain ? e->Hx + MM : e->Hx;                // distance-weighted Grams, one per input dim
+        const double* gd = e->gvec + gstride;                         // g^{d_i} follow g^mu
+        dim3 grid((unsigned)hm_cdiv(M, 8), (unsigned)Q);
+        gram_dz_kernel<<<grid, 256, 0, s>>>(e->C, e->alpha, e->Zp, e->consts, Hc1, Dx, MM, gd, gstride, stats + e->off_dz, M, Mp, Xd);
+        HM_CUDA(cudaGetLastError());
     }
     return 0;
 }
@@ -599,6 +746,7 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
     if (J > HM_MAXJ) { hm_set_error("J=%d output functions > %d", J, HM_MAXJ); delete e; return HMOGP_ERR_ARG; }
     e->J = J;
     e->tk.T = e->T; e->tk.Q = e->Q; e->tk.Xdim = e->Xd; e->tk.J = J;
+    e->tk.acs = (e->prec == HMOGP_PREC_TC ? 4 : 2) * e->Q;
     if (e->prec == HMOGP_PREC_TC && !hm_tc_available()) { hm_set_error("tensor-core path not built"); delete e; return HMOGP_ERR_ARG; }
     int rc = 0;
 #define A_(ptr, n) if (!rc) rc = dalloc(e, &e->ptr, (size_t)(n))
@@ -610,8 +758,36 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
     A_(Kuu, MM); A_(Luu, MM); A_(LuuInv, MM); A_(Ki, MM); A_(Lu, MM); A_(LuInv, MM); A_(Sinv, MM); A_(S, MM); A_(SK, MM);
     A_(KSK, MM); A_(C, MM); A_(tmp, MM); A_(T1, MM); A_(E, MM); A_(tmpE, MM); A_(dLdS, MM); A_(dLdLfull, MM); A_(dLdK, MM);
     A_(Cf, MM);
-    e->Cb = nullptr;
-    if (!rc && e->prec == HMOGP_PREC_TC) { unsigned short* cb = nullptr; rc = dalloc(e, &cb, 2 * MM + 2 * Q * Mp); e->Cb = cb; }
+    e->Cb = nullptr; e->tcinfo = nullptr; e->jobs_d = nullptr; e->segs_d = nullptr; e->segoff_d = nullptr; e->jobslots_d = nullptr;
+    e->slots = nullptr; e->Hx = nullptr; e->gvec = nullptr; e->plan_dirty = true;
+    e->nworkers = hm_proj_workers(e->prec, e->Mc);
+    if (!rc && e->prec == HMOGP_PREC_TC) {
+        const char* ev = getenv("HMOGP_TC_NPASS");
+        e->tc_npass = ev ? atoi(ev) : 3;
+        if (e->tc_npass < 1 || e->tc_npass > 3) e->tc_npass = 3;
+        ev = getenv("HMOGP_TC_FLUSH_ROWS");
+        e->tc_flush = (ev ? atoi(ev) : 4096) / HM_GRAM_CHUNK;
+        if (e->tc_flush < 1) e->tc_flush = 1;
+        unsigned short* cb = nullptr;
+        rc = dalloc(e, &cb, hm_tc_image_elems(e->Mc, e->Q));
+        e->Cb = cb;
+        A_(tcinfo, 1);
+        // output tiles of the lower block-triangle of an Mc x Mc Gram: rows [128 I, +128) x columns in pieces of <= 256
+        for (int I = 0; I < e->Mc / 128; ++I)
+            for (int j0 = 0; j0 < (I + 1) * 128; j0 += 256) {
+                HmGramJob jb; jb.I = I; jb.j0 = j0; jb.nw = ((I + 1) * 128 - j0) < 256 ? ((I + 1) * 128 - j0) : 256;
+                e->jobs_h.push_back(jb);
+            }
+        const size_t nj = e->jobs_h.size();
+        e->max_segs = (int)(e->nworkers + Q * nj + 8);
+        e->nslots_max = e->max_segs;
+        A_(jobs_d, nj); A_(segs_d, e->max_segs); A_(segoff_d, e->nworkers + 1); A_(jobslots_d, Q * nj);
+        A_(slots, (size_t)e->nslots_max * HM_GRAM_SLOT_DOUBLES);
+        A_(Hx, (size_t)(1 + Xd) * MM);
+        A_(gvec, (size_t)HM_GRAM_MAXV * Q * Mp);
+        if (!rc && cudaMemcpy(e->jobs_d, e->jobs_h.data(), sizeof(HmGramJob) * nj, cudaMemcpyHostToDevice) != cudaSuccess) rc = HMOGP_ERR_CUDA;
+        if (!rc && cudaMemset(e->tcinfo, 0, sizeof(HmTcInfo)) != cudaSuccess) rc = HMOGP_ERR_CUDA;
+    }
     A_(KLq, HM_MAXQ); A_(jitter_d, HM_MAXQ); A_(rowstat, Q * Mp * 2); A_(dzmm, Q * Xd * Mp); A_(flags_d, 2 * HM_MAXQ);
     // statistics layout
     e->off_nneg = (int)T; e->off_sdv = 2 * (int)T; e->off_sma = e->off_sdv + J; e->off_svc = e->off_sma + J * (int)Q;
@@ -621,8 +797,7 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
     e->stats_len = (int64_t)e->off_H + (int64_t)MM;
     A_(stats, e->stats_len);
     e->lik_max_blocks = 148 * 8;
-    A_(lik_part, (size_t)e->lik_max_blocks * (2 + HM_MAXF * (1 + 2 * HM_MAXQ)));
-    e->nworkers = hm_proj_workers(e->prec, e->Mc);
+    A_(lik_part, (size_t)e->lik_max_blocks * (2 + HM_MAXF * (1 + 2 * HM_MAXQ) + HM_MAXQ));
     A_(colpart, Q * e->nworkers * ((1 + Xd) * e->Mc + 1));
     e->nsplit = hm_gram_splits(e->prec, e->Mc, e->Q);
     A_(Hpart, (size_t)e->nsplit * Q * e->Mc * e->Mc);
@@ -672,7 +847,7 @@ int hmogp_set_data(hmogp_engine* e, int32_t t, const double* X, const double* Y,
         const size_t n = N > 0 ? (size_t)N : 1;
         HM_CUDA(cudaMalloc((void**)&e->Xd_[t], n * e->Xd * sizeof(double)));
         HM_CUDA(cudaMalloc((void**)&e->Yd_[t], n * sizeof(double)));
-        HM_CUDA(cudaMalloc(&e->tk.AC[t], n * 2 * e->Q * esize(e->prec)));
+        HM_CUDA(cudaMalloc(&e->tk.AC[t], n * e->tk.acs * esize(e->prec)));
         HM_CUDA(cudaMalloc(&e->tk.MW[t], n * 4 * e->Q * esize(e->prec)));
         e->cap[t] = N;
     }
@@ -684,6 +859,7 @@ int hmogp_set_data(hmogp_engine* e, int32_t t, const double* X, const double* Y,
     e->N[t] = N;
     e->tk.begin[t] = 0;
     e->tk.count[t] = N;
+    e->plan_dirty = true;
     return 0;
 }
 
@@ -695,6 +871,7 @@ int hmogp_set_rows(hmogp_engine* e, const int64_t* begin, const int64_t* count) 
         e->tk.begin[t] = b;
         e->tk.count[t] = c;
     }
+    e->plan_dirty = true;
     return 0;
 }
 
@@ -715,24 +892,31 @@ int hmogp_step_local(hmogp_engine* e, const hmogp_params* p, int32_t mem_kind, i
     if (e->timing) HM_CUDA(cudaEventRecord(e->ev[1], s));
     HM_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (what >= HMOGP_WHAT_VE ? (int64_t)e->off_H : e->stats_len), s));
     HmProjArgs pa = proj_args(e);
+    const bool tc = e->prec == HMOGP_PREC_TC;
     // ---- forward projections
-    if (e->prec == HMOGP_PREC_TC) HM_CHECK(hm_tc_proj_fwd(s, e->tk, pa, e->Cb));
-    else HM_CHECK(hm_proj_fwd(s, e->prec, e->tk, pa));
+    if (tc) {
+        HM_CUDA(cudaMemsetAsync(&e->tcinfo->wmax[0][0], 0, sizeof(unsigned) * 2 * HM_MAXQ, s));
+        HM_CHECK(hm_tc_proj_fwd(s, e->tk, pa, e->Cb, e->tcinfo, what >= HMOGP_WHAT_FULL, e->tc_npass));
+    } else HM_CHECK(hm_proj_fwd(s, e->prec, e->tk, pa));
     if (e->timing) HM_CUDA(cudaEventRecord(e->ev[2], s));
     // ---- likelihoods
     const int simt_prec = (e->prec == HMOGP_PREC_FP64) ? HMOGP_PREC_FP64 : HMOGP_PREC_FP32;
     for (int t = 0; t < e->T; ++t) {
         int nb = 0;
         HM_CHECK(hm_lik_rows(s, simt_prec, e->tk, e->consts, t, what >= HMOGP_WHAT_VE, e->has_chain, e->lik_part,
-                             e->lik_max_blocks, &nb, nullptr, nullptr, nullptr, nullptr, nullptr));
-        const int nstat = 2 + e->tk.dimf[t] * (1 + 2 * e->Q);
+                             e->lik_max_blocks, &nb, nullptr, nullptr, nullptr, nullptr, nullptr, tc ? e->tcinfo : nullptr,
+                             what >= HMOGP_WHAT_FULL));
+        const int nstat = 2 + e->tk.dimf[t] * (1 + 2 * e->Q) + (tc ? e->Q : 0);
         reduce_lik_kernel<<<1, 128, 0, s>>>(e->lik_part, nb, nstat, stats, t, e->T, e->J, e->Q, e->tk.foff[t], e->tk.dimf[t],
-                                            e->off_sdv, e->off_sma, e->off_svc);
+                                            e->off_sdv, e->off_sma, e->off_svc, e->off_dls);
         HM_CUDA(cudaGetLastError());
     }
     if (e->timing) HM_CUDA(cudaEventRecord(e->ev[3], s));
     // ---- backward statistics
-    if (what >= HMOGP_WHAT_VE) {
+    if (what >= HMOGP_WHAT_VE && tc) {
+        if (e->timing) HM_CUDA(cudaEventRecord(e->ev[4], s));
+        HM_CHECK(tc_backward(e, what, stats));
+    } else if (what >= HMOGP_WHAT_VE) {
         HM_CHECK(hm_proj_bwd(s, simt_prec, e->tk, pa, what >= HMOGP_WHAT_FULL));
         const int ncol = (1 + e->Xd) * e->Mc + 1;
         dim3 g1((unsigned)hm_cdiv(ncol, 256), (unsigned)e->Q);
@@ -872,7 +1056,7 @@ int hmogp_get_rows(hmogp_engine* e, int32_t t, double* m_fd, double* v_fd, doubl
     int nb = 0;
     const int simt_prec = (e->prec == HMOGP_PREC_FP64) ? HMOGP_PREC_FP64 : HMOGP_PREC_FP32;
     double* part = nullptr;
-    HM_CUDA(cudaMalloc((void**)&part, sizeof(double) * e->lik_max_blocks * (2 + HM_MAXF * (1 + 2 * HM_MAXQ))));
+    HM_CUDA(cudaMalloc((void**)&part, sizeof(double) * e->lik_max_blocks * (2 + HM_MAXF * (1 + 2 * HM_MAXQ) + HM_MAXQ)));
     HmTasks tk = e->tk;
     void* mwtmp = nullptr;  // do not disturb the row weights of the last evaluation
     HM_CUDA(cudaMalloc(&mwtmp, (size_t)n * 4 * e->Q * esize(e->prec)));

@@ -30,7 +30,7 @@ int hm_upload_gh_tables() {
 }
 
 #define HM_LIK_THREADS 128
-#define HM_LIK_MAXSTAT (2 + HM_MAXF * (1 + 2 * HM_MAXQ))
+#define HM_LIK_MAXSTAT (2 + HM_MAXF * (1 + 2 * HM_MAXQ) + HM_MAXQ)
 
 struct HmLikRowArgs {
     int kind, K, dimf, foff, Q, t;
@@ -42,14 +42,20 @@ struct HmLikRowArgs {
     const HmConsts* consts;
     double* partials;  // [gridDim.x][nstat]
     int want_grads, has_chain;
+    int acs;           // AC row stride (elements)
+    int hyper;         // AC rows carry valid (b, e) (full step on the tensor-core path)
+    HmTcInfo* tcinfo;  // tensor-core path: AC rows carry (a, c, b, e); emit the K_mn lengthscale statistic and max |omega|
     double *rows_m, *rows_v, *rows_ve, *rows_dm, *rows_dv;
 };
 
 template <typename T>
 __global__ void __launch_bounds__(HM_LIK_THREADS) lik_rows_kernel(HmLikRowArgs p) {
     __shared__ double sacc[HM_LIK_THREADS / 32][HM_LIK_MAXSTAT];
-    const int nstat = 2 + p.dimf * (1 + 2 * p.Q);
+    const int nbase = 2 + p.dimf * (1 + 2 * p.Q);
+    const int nstat = nbase + (p.tcinfo ? p.Q : 0);
     const HmConsts* __restrict__ cs = p.consts;
+    float wmax[2][HM_MAXQ];
+    for (int q = 0; q < HM_MAXQ; ++q) { wmax[0][q] = 0.f; wmax[1][q] = 0.f; }
     const int Q = p.Q, F = p.dimf;
     const T bs = T(cs->bscale[p.t]);
     double st[HM_LIK_MAXSTAT];
@@ -57,7 +63,7 @@ __global__ void __launch_bounds__(HM_LIK_THREADS) lik_rows_kernel(HmLikRowArgs p
 
     for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < p.count;
          row += (int64_t)gridDim.x * blockDim.x) {
-        const T* ac = reinterpret_cast<const T*>(p.AC) + row * 2 * Q;
+        const T* ac = reinterpret_cast<const T*>(p.AC) + row * p.acs;
         T a[HM_MAXQ], c[HM_MAXQ];
         for (int q = 0; q < Q; ++q) { a[q] = ac[q]; c[q] = ac[Q + q]; }
         T m[HM_MAXF], v[HM_MAXF];
@@ -105,6 +111,12 @@ __global__ void __launch_bounds__(HM_LIK_THREADS) lik_rows_kernel(HmLikRowArgs p
                 mw[Q + q] = om;
                 mw[2 * Q + q] = muc;
                 mw[3 * Q + q] = omc;
+                if (p.tcinfo) {
+                    // sum_m GK[n,m] |x_n - z_m|^2 = mu^c b + 2 omega^c e   (b, e from the forward epilogue, tc_fwd.cu)
+                    if (p.hyper) st[nbase + q] += (double)(muc * ac[2 * Q + q] + T(2) * omc * ac[3 * Q + q]);
+                    wmax[0][q] = fmaxf(wmax[0][q], fabsf((float)om));
+                    wmax[1][q] = fmaxf(wmax[1][q], fabsf((float)omc));
+                }
             }
         }
         if (p.rows_m) {
@@ -115,6 +127,16 @@ __global__ void __launch_bounds__(HM_LIK_THREADS) lik_rows_kernel(HmLikRowArgs p
                 p.rows_dv[row * F + f] = (double)o.dv[f];
             }
             p.rows_ve[row] = (double)o.ve;
+        }
+    }
+    if (p.tcinfo && p.want_grads) {
+        for (int q = 0; q < Q; ++q) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                float m = wmax[k][q];
+                for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+                if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(&p.tcinfo->wmax[k][q], __float_as_uint(m));
+            }
         }
     }
     // block reduction in a fixed order (deterministic): warp shuffles, then per-warp slots summed by one thread
@@ -134,7 +156,7 @@ __global__ void __launch_bounds__(HM_LIK_THREADS) lik_rows_kernel(HmLikRowArgs p
 
 int hm_lik_rows(cudaStream_t s, int prec, const HmTasks& tk, const HmConsts* consts, int t, bool want_grads,
                 bool has_chain, double* partials, int max_blocks, int* nblocks_out, double* rows_m, double* rows_v,
-                double* rows_ve, double* rows_dm, double* rows_dv) {
+                double* rows_ve, double* rows_dm, double* rows_dv, HmTcInfo* tcinfo, bool hyper) {
     HmLikRowArgs p;
     p.kind = tk.kind[t]; p.K = tk.K[t]; p.dimf = tk.dimf[t]; p.foff = tk.foff[t]; p.Q = tk.Q; p.t = t;
     p.sigma = tk.sigma[t];
@@ -142,6 +164,7 @@ int hm_lik_rows(cudaStream_t s, int prec, const HmTasks& tk, const HmConsts* con
     p.Y = tk.Y[t]; p.AC = tk.AC[t]; p.MW = tk.MW[t];
     p.consts = consts; p.partials = partials;
     p.want_grads = want_grads ? 1 : 0; p.has_chain = has_chain ? 1 : 0;
+    p.acs = tk.acs; p.tcinfo = tcinfo; p.hyper = hyper ? 1 : 0;
     p.rows_m = rows_m; p.rows_v = rows_v; p.rows_ve = rows_ve; p.rows_dm = rows_dm; p.rows_dv = rows_dv;
     int64_t nb = hm_cdiv(p.count, HM_LIK_THREADS);
     if (nb > max_blocks) nb = max_blocks;

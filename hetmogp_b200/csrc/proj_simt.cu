@@ -251,8 +251,8 @@ __global__ void __launch_bounds__(kThreads, 1) proj_kernel(HmTasks tk, HmProjArg
             __syncthreads();
             T* ac = reinterpret_cast<T*>(tk.AC[t]);
             for (int r = tid; r < tr.nrows; r += kThreads) {
-                ac[(tr.row0 + r) * 2 * Q + q] = T(racc[r]);
-                ac[(tr.row0 + r) * 2 * Q + Q + q] = T(racc[BM + r]);
+                ac[(tr.row0 + r) * tk.acs + q] = T(racc[r]);
+                ac[(tr.row0 + r) * tk.acs + Q + q] = T(racc[BM + r]);
             }
         }
         __syncthreads();

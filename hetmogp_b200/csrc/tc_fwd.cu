@@ -1,0 +1,413 @@
+// Forward projection on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a only.
+//
+// Contraction (reference: /root/reference/hetmogp/svmogp_inf.py:212-218 restated), per latent q and
+// 128-row tile of task t, with K = k_q(X_t, Z_q) generated on the fly (reference materialises it: util.py:145-164):
+//     P = K C_q                       tcgen05.mma, split-fp16 operands (3 products), fp32 accumulators in TMEM
+//     c_tq[n] = sum_j P[n,j] K[n,j]   a_tq[n] = K[n,:] . alpha_q                                   (epilogue)
+//     b_tq[n] = sum_j alpha_j K[n,j] |x_n - z_j|^2     e_tq[n] = sum_j P[n,j] K[n,j] |x_n - z_j|^2   (hyper only)
+// b, e are the per-row scalars from which the lengthscale gradient of the K_mn chain (svmogp.py:139-141, GPy
+// RBF.update_gradients_full) follows without a second contraction:  d l_q = (1/l^3) sum_n mu^c b + 2 omega^c e.
+//
+// Warp roles (576 threads, 1 CTA/SM, persistent over row tiles; grid.y = latent q):
+//   warps 0-7   generators : K tile of this stage (128 rows x 64 inducing points; warp = 32 rows x 32 columns): one
+//                            MUFU ex2 per entry, split into fp16 hi/lo, stored straight into the SWIZZLE_128B K-major
+//                            smem image the MMA reads
+//   warps 8-15  epilogue   : tcgen05.ld the 128x256 fp32 accumulator (thread = row = TMEM lane, warp = 32 lanes x 128
+//                            columns), multiply by the regenerated K entries, reduce along the row
+//   warp  16    MMA issuer : one thread, 12 tcgen05.mma (M128 N256 K16) per stage, tcgen05.commit -> mbarriers
+//   warp  17    bulk copy  : cp.async.bulk of the pre-swizzled C_q operand image (hi+lo, 64 KB per stage) from L2
+// Rings: 2 smem stages (96 KB each) full/empty, 2 TMEM accumulators (2 x 256 columns) full/empty.
+#include "tc_common.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int kRows = 128;   // UMMA M
+constexpr int kNB = 256;     // UMMA N (output columns per job)
+constexpr int kKB = 64;      // inducing points per stage (128 B of fp16 = one swizzle-atom row)
+constexpr int kStages = 2;
+constexpr int kAHalf = kRows * 128;                    // 16 KB : A hi (or lo) image of one stage
+constexpr int kBHalf = kNB * 128;                      // 32 KB : B hi (or lo) image of one stage
+constexpr int kStageBytes = 2 * kAHalf + 2 * kBHalf;   // 96 KB
+constexpr int kGenWarps = 8, kEpiWarps = 8, kMmaWarp = 16;   // + bulk-copy warp 17
+constexpr int kThreads = 576;
+constexpr uint32_t kIdesc = idesc_f16(kRows, kNB);
+
+struct TileRef { int t; int64_t row0; int nrows; };
+__device__ __forceinline__ TileRef find_tile(const HmTasks& tk, int64_t tile) {
+    TileRef r; r.t = 0; r.row0 = 0; r.nrows = 0;
+    for (int t = 0; t < tk.T; ++t) {
+        const int64_t nt = (tk.count[t] + kRows - 1) / kRows;
+        if (tile < nt) {
+            r.t = t; r.row0 = tile * kRows;
+            const int64_t rem = tk.count[t] - r.row0;
+            r.nrows = rem < kRows ? (int)rem : kRows;
+            return r;
+        }
+        tile -= nt;
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------- scales
+// One block per q:  cexp from max |C_q|, kexp from sigma_q^2.
+__global__ void tc_scale_kernel(const double* __restrict__ C, const HmConsts* __restrict__ cs, HmTcInfo* info, int M, int Mp) {
+    const int q = blockIdx.x;
+    float mx = 0.f;
+    for (int64_t e = threadIdx.x; e < (int64_t)M * M; e += blockDim.x) {
+        const int i = (int)(e / M), j = (int)(e % M);
+        mx = fmaxf(mx, fabsf((float)C[((size_t)q * Mp + i) * Mp + j]));
+    }
+    __shared__ float sh[32];
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)blockDim.x / 32; ++w) mx = fmaxf(mx, sh[w]);
+        int e = 0;
+        if (mx > 0.f && isfinite(mx)) frexpf(mx, &e);          // mx < 2^e
+        info->cexp[q] = (mx > 0.f && isfinite(mx)) ? 14 - e : 0;
+        int ev = 0;
+        const float v = (float)cs->var[q];
+        if (v > 0.f && isfinite(v)) frexpf(v, &ev);
+        info->kexp[q] = (v > 0.f && isfinite(v)) ? 12 - ev : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- operand image of C_q
+// Cb layout: [q][h = column block of 256][kb = k block of 64] { hi image (256 rows x 128 B, SW128), lo image }.
+// Row j of an image holds B[j][k] = 2^cexp C_q[h*256 + j][kb*64 + k]; 16-byte chunk c of row j sits at chunk (c ^ (j & 7)).
+__global__ void tc_image_kernel(const double* __restrict__ C, const HmTcInfo* __restrict__ info, uint16_t* __restrict__ Cb,
+                                int Mp, int Mc) {
+    const int q = blockIdx.z;
+    const int nkb = Mc / kKB;
+    const int h = blockIdx.y / nkb, kb = blockIdx.y % nkb;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;   // (row j, chunk c)
+    if (e >= kNB * 8) return;
+    const int j = e >> 3, c = e & 7;
+    const double sc = ldexp(1.0, info->cexp[q]);
+    const double* src = C + ((size_t)q * Mp + (size_t)(h * kNB + j)) * Mp + kb * kKB + c * 8;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) split2((float)(src[2 * p] * sc), (float)(src[2 * p + 1] * sc), hi[p], lo[p]);
+    uint8_t* img = reinterpret_cast<uint8_t*>(Cb) + ((size_t)(q * (Mc / kNB) + h) * nkb + kb) * (2 * kBHalf);
+    const int off = j * 128 + ((c ^ (j & 7)) << 4);
+    *reinterpret_cast<uint4*>(img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(img + kBHalf + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// ------------------------------------------------------------------------------------------- forward kernel
+struct FwdBars {
+    uint64_t full[kStages], empty[kStages], tfull[2], tempty[2];
+    uint32_t tmem_base;
+};
+
+// compensated fp32 accumulation (TwoSum): the fp64 pipe is too slow to sit in the epilogue loop
+__device__ __forceinline__ void two_sum_add(float& hi, float& lo, float x) {
+    const float s = hi + x;
+    const float bp = s - hi;
+    lo += (hi - (s - bp)) + (x - bp);
+    hi = s;
+}
+
+// Per-column constants, grouped by 8 columns so that one thread fetches them with 128-bit loads:
+//   tab[chunk8][row][8]   rows: 2i = -s z_i (hi), 2i+1 = -s z_i (lo), 2XD = -(log2 sigma^2 + kexp) (generator bias),
+//                               2XD+1 = -log2 sigma^2 (epilogue bias), 2XD+2 = alpha_q;  padded columns: biases +1e30
+// (negated so that the packed loops are pure FADD2 / FFMA2:  K = ex2(-(d.d - bias)))
+template <int XD> struct FwdTab { static constexpr int R = 2 * XD + 3; };
+
+template <int XD>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const HmTcInfo* __restrict__ info, int64_t ntiles,
+              int hyper, int npass) {
+    constexpr int R = FwdTab<XD>::R;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // SWIZZLE_128B operand images need a 1024-byte aligned base: align by hand (the launch reserves the slack)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int Mc = pa.Mc, Mp = pa.Mp, M = pa.M, Q = pa.Q;
+    const int q = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nhalf = Mc / kNB, nkb = Mc / kKB;
+
+    uint8_t* stage_base = smem;                                                   // kStages * 96 KB, 1024-aligned
+    float* tab = reinterpret_cast<float*>(smem + kStages * kStageBytes);          // [Mc/8][R][8]
+    float* xch = tab + (size_t)Mc * R;                                            // [2][4][128] epilogue half-row exchange
+    FwdBars* sb = reinterpret_cast<FwdBars*>(xch + 2 * 4 * 128);
+
+    const HmConsts* __restrict__ cs = pa.consts;
+    const double s2 = 0.5 * 1.4426950408889634 * cs->inv_l2[q];                   // 2^(-s2 d^2) = exp(-d^2 / (2 l^2))
+    const double sscale = sqrt(s2);
+    const int kexp = info->kexp[q], cexp = info->cexp[q];
+    for (int m = threadIdx.x; m < Mc; m += kThreads) {
+        float* t8 = tab + (size_t)(m >> 3) * R * 8 + (m & 7);
+        for (int i = 0; i < XD; ++i) {
+            const double z = (m < M) ? pa.Zp[((size_t)q * Mp + m) * XD + i] : 0.0;
+            float h, l;
+            split_scaled(z, sscale, h, l);
+            t8[(2 * i) * 8] = -h;
+            t8[(2 * i + 1) * 8] = -l;
+        }
+        const float lv = (float)log2(cs->var[q]);
+        t8[(2 * XD) * 8] = (m < M) ? -(lv + (float)kexp) : 1.0e30f;
+        t8[(2 * XD + 1) * 8] = (m < M) ? -lv : 1.0e30f;
+        t8[(2 * XD + 2) * 8] = (m < M) ? (float)pa.alpha[(size_t)q * Mp + m] : 0.f;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&sb->full[s], kGenWarps + 1); mbar_init(&sb->empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&sb->tfull[b], 1); mbar_init(&sb->tempty[b], kEpiWarps); }
+        mbar_fence_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(&sb->tmem_base, 512u);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = sb->tmem_base;
+
+    if (warp < kGenWarps) {
+        // ======================================================= generators: thread = row, warp = (row quadrant, column half)
+        const int r = (warp & 3) * 32 + lane, ch = warp >> 2;
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const TileRef tr = find_tile(tk, tile);
+            float xh[XD], xl[XD];
+#pragma unroll
+            for (int i = 0; i < XD; ++i) {
+                const double x = (r < tr.nrows) ? tk.X[tr.t][(tk.begin[tr.t] + tr.row0 + r) * XD + i] : 0.0;
+                split_scaled(x, sscale, xh[i], xl[i]);
+            }
+            for (int h = 0; h < nhalf; ++h) {
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait_warp(&sb->empty[stage], phase ^ 1);
+                    uint8_t* a_hi = stage_base + (size_t)stage * kStageBytes + r * 128;
+                    uint8_t* a_lo = a_hi + kAHalf;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int c = ch * 4 + cc;
+                        const float4* t4 = reinterpret_cast<const float4*>(tab + (size_t)(kb * 8 + c) * R * 8);
+                        float2 e[4];   // d.d - bias for the 8 columns, as 4 pairs
+                        {
+                            const float4 b0 = t4[(2 * XD) * 2], b1 = t4[(2 * XD) * 2 + 1];
+                            e[0] = make_float2(b0.x, b0.y); e[1] = make_float2(b0.z, b0.w);
+                            e[2] = make_float2(b1.x, b1.y); e[3] = make_float2(b1.z, b1.w);
+                        }
+#pragma unroll
+                        for (int i = 0; i < XD; ++i) {
+                            const float4 h0 = t4[(2 * i) * 2], h1 = t4[(2 * i) * 2 + 1];
+                            const float4 l0 = t4[(2 * i + 1) * 2], l1 = t4[(2 * i + 1) * 2 + 1];
+                            const float2 nzh[4] = {make_float2(h0.x, h0.y), make_float2(h0.z, h0.w), make_float2(h1.x, h1.y), make_float2(h1.z, h1.w)};
+                            const float2 nzl[4] = {make_float2(l0.x, l0.y), make_float2(l0.z, l0.w), make_float2(l1.x, l1.y), make_float2(l1.z, l1.w)};
+                            const float2 xh2 = dup2(xh[i]), xl2 = dup2(xl[i]);
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) {
+                                const float2 d = add2(add2(xh2, nzh[p]), add2(xl2, nzl[p]));
+                                e[p] = fma2(d, d, e[p]);
+                            }
+                        }
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) split2(ex2(-e[p].x), ex2(-e[p].y), hi[p], lo[p]);
+                        const int off = (c ^ (r & 7)) << 4;
+                        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                    fence_async_smem();            // generic-proxy stores -> visible to the tensor-core (async) proxy
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sb->full[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp < kGenWarps + kEpiWarps) {
+        // ======================================================= epilogue: thread = row = TMEM lane, warp = (lane quadrant, column half)
+        const int ew = warp - kGenWarps, lq = ew & 3, ch = ew >> 2, r = lq * 32 + lane;
+        const float inv_pc = pow2i(-(kexp + cexp));      // undo the operand scales of P
+        const float inv_s2 = (float)(1.0 / s2);           // scaled squared distance -> |x - z|^2
+        uint32_t jc = 0, tcount = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+            const TileRef tr = find_tile(tk, tile);
+            float xh[XD], xl[XD];
+#pragma unroll
+            for (int i = 0; i < XD; ++i) {
+                const double x = (r < tr.nrows) ? tk.X[tr.t][(tk.begin[tr.t] + tr.row0 + r) * XD + i] : 0.0;
+                split_scaled(x, sscale, xh[i], xl[i]);
+            }
+            float ah = 0.f, al = 0.f, chh = 0.f, cl = 0.f, bh = 0.f, bl = 0.f, eh = 0.f, el = 0.f;
+            for (int h = 0; h < nhalf; ++h, ++jc) {
+                const uint32_t buf = jc & 1u;
+                mbar_wait_warp(&sb->tfull[buf], (jc >> 1) & 1u);
+                fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + buf * kNB + ch * (kNB / 2);
+#pragma unroll 1
+                for (int cc = 0; cc < kNB / 64; ++cc) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + cc * 32, v);
+                    tmem_ld_wait();
+                    float2 a2 = dup2(0.f), c2 = dup2(0.f), b2 = dup2(0.f), e2 = dup2(0.f);
+                    const int m0 = h * kNB + ch * (kNB / 2) + cc * 32;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float4* t4 = reinterpret_cast<const float4*>(tab + (size_t)((m0 >> 3) + g) * R * 8);
+                        float2 u[4];
+#pragma unroll
+                        for (int i = 0; i < XD; ++i) {
+                            const float4 h0 = t4[(2 * i) * 2], h1 = t4[(2 * i) * 2 + 1];
+                            const float4 l0 = t4[(2 * i + 1) * 2], l1 = t4[(2 * i + 1) * 2 + 1];
+                            const float2 nzh[4] = {make_float2(h0.x, h0.y), make_float2(h0.z, h0.w), make_float2(h1.x, h1.y), make_float2(h1.z, h1.w)};
+                            const float2 nzl[4] = {make_float2(l0.x, l0.y), make_float2(l0.z, l0.w), make_float2(l1.x, l1.y), make_float2(l1.z, l1.w)};
+                            const float2 xh2 = dup2(xh[i]), xl2 = dup2(xl[i]);
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) {
+                                const float2 d = add2(add2(xh2, nzh[p]), add2(xl2, nzl[p]));
+                                u[p] = (i == 0) ? mul2(d, d) : fma2(d, d, u[p]);
+                            }
+                        }
+                        const float4 b0 = t4[(2 * XD + 1) * 2], b1 = t4[(2 * XD + 1) * 2 + 1];
+                        const float4 q0 = t4[(2 * XD + 2) * 2], q1 = t4[(2 * XD + 2) * 2 + 1];
+                        const float2 nb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+                        const float2 aa[4] = {make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y), make_float2(q1.z, q1.w)};
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            const float2 ea = add2(u[p], nb[p]);                       // d.d - log2 sigma^2
+                            const float2 kv = make_float2(ex2(-ea.x), ex2(-ea.y));
+                            const float2 pk = mul2(make_float2(__uint_as_float(v[g * 8 + 2 * p]), __uint_as_float(v[g * 8 + 2 * p + 1])), kv);
+                            const float2 ak = mul2(kv, aa[p]);
+                            c2 = add2(c2, pk);
+                            a2 = add2(a2, ak);
+                            if (hyper) {
+                                e2 = fma2(pk, u[p], e2);
+                                b2 = fma2(ak, u[p], b2);
+                            }
+                        }
+                    }
+                    const float a32 = a2.x + a2.y, c32 = c2.x + c2.y, b32 = b2.x + b2.y, e32 = e2.x + e2.y;
+                    two_sum_add(ah, al, a32);
+                    two_sum_add(chh, cl, c32);
+                    if (hyper) { two_sum_add(bh, bl, b32); two_sum_add(eh, el, e32); }
+                }
+                fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sb->tempty[buf]);
+            }
+            // combine the two column halves of each row: half 1 -> smem -> half 0 -> HBM
+            float* xb = xch + (tcount & 1u) * 4 * 128;
+            if (ch == 1) {
+                xb[r] = ah + al; xb[128 + r] = chh + cl; xb[256 + r] = bh + bl; xb[384 + r] = eh + el;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+            if (ch == 0 && r < tr.nrows) {
+                float* ac = reinterpret_cast<float*>(tk.AC[tr.t]) + (tr.row0 + r) * tk.acs;
+                ac[q] = (ah + al) + xb[r];
+                ac[Q + q] = ((chh + cl) + xb[128 + r]) * inv_pc;
+                if (hyper) {
+                    ac[2 * Q + q] = ((bh + bl) + xb[256 + r]) * inv_s2;
+                    ac[3 * Q + q] = ((eh + el) + xb[384 + r]) * inv_pc * inv_s2;
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ======================================================= MMA issuer (one thread)
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0, jc = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int h = 0; h < nhalf; ++h, ++jc) {
+                    const uint32_t buf = jc & 1u;
+                    mbar_wait(&sb->tempty[buf], ((jc >> 1) & 1u) ^ 1u);
+                    fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * kNB;
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(&sb->full[stage], phase);
+                        fence_after();
+                        const uint32_t sa = smem_u32(stage_base + (size_t)stage * kStageBytes);
+                        const uint64_t a_hi = desc_sw128(sa), a_lo = desc_sw128(sa + kAHalf);
+                        const uint64_t b_hi = desc_sw128(sa + 2 * kAHalf), b_lo = desc_sw128(sa + 2 * kAHalf + kBHalf);
+#pragma unroll
+                        for (int ks = 0; ks < kKB / 16; ++ks) {
+                            const uint64_t adv = (uint64_t)(ks * 2);   // 32 bytes per K=16 step, in 16-byte units
+                            mma_f16(d_tmem, a_hi + adv, b_hi + adv, kIdesc, (kb | ks) ? 1u : 0u);
+                            if (npass >= 2) mma_f16(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
+                            if (npass >= 3) mma_f16(d_tmem, a_lo + adv, b_hi + adv, kIdesc, 1u);
+                        }
+                        commit(&sb->empty[stage]);      // frees the smem stage when these MMAs have read it
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                    commit(&sb->tfull[buf]);            // accumulator of this job complete
+                }
+            }
+        }
+    } else {
+        // ======================================================= bulk-copy producer (one thread)
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int h = 0; h < nhalf; ++h) {
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(&sb->empty[stage], phase ^ 1);
+                        uint8_t* dst = stage_base + (size_t)stage * kStageBytes + 2 * kAHalf;
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(Cb) + ((size_t)(q * nhalf + h) * nkb + kb) * (2 * kBHalf);
+                        mbar_expect_tx(&sb->full[stage], 2 * kBHalf);
+#pragma unroll
+                        for (int part = 0; part < 4; ++part)
+                            bulk_g2s(dst + part * (kBHalf / 2), src + part * (kBHalf / 2), kBHalf / 2, &sb->full[stage]);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    }
+    // ---- teardown
+    fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512u);
+}
+
+size_t fwd_smem_bytes(int Mc, int Xd) {
+    return (size_t)kStages * kStageBytes + sizeof(float) * ((size_t)Mc * (2 * Xd + 3) + 2 * 4 * 128) + sizeof(FwdBars) + 64 + 1024;
+}
+
+template <int XD>
+int launch_fwd(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const void* Cb, const HmTcInfo* info, int64_t ntiles,
+               bool hyper, int npass) {
+    const size_t smem = fwd_smem_bytes(a.Mc, XD);
+    if (smem > 227 * 1024) {
+        hm_set_error("tensor-core projection: M=%d (padded %d) with Xdim=%d needs %zu B of shared memory", a.M, a.Mc, XD, smem);
+        return HMOGP_ERR_ARG;
+    }
+    HM_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<XD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nw = a.nworkers;
+    if (ntiles < nw) nw = (int)ntiles;
+    dim3 grid((unsigned)nw, (unsigned)a.Q);
+    tc_fwd_kernel<XD><<<grid, kThreads, smem, s>>>(tk, a, reinterpret_cast<const uint16_t*>(Cb), info, ntiles, hyper ? 1 : 0, npass);
+    HM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int hm_tc_available() { return 1; }
+
+size_t hm_tc_image_elems(int Mc, int Q) { return (size_t)Q * Mc * Mc * 2; }   // fp16 elements (hi + lo)
+
+int hm_tc_prepare(cudaStream_t s, const double* C, const HmConsts* consts, HmTcInfo* info, void* Cb, int M, int Mp, int Mc, int Q) {
+    tc_scale_kernel<<<Q, 1024, 0, s>>>(C, consts, info, M, Mp);
+    HM_CUDA(cudaGetLastError());
+    dim3 grid((unsigned)hm_cdiv(kNB * 8, 256), (unsigned)((Mc / kNB) * (Mc / kKB)), (unsigned)Q);
+    tc_image_kernel<<<grid, 256, 0, s>>>(C, info, reinterpret_cast<uint16_t*>(Cb), Mp, Mc);
+    HM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int hm_tc_proj_fwd(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const void* Cb, const HmTcInfo* info, bool hyper,
+                   int npass) {
+    int64_t ntiles = 0;
+    for (int t = 0; t < tk.T; ++t) ntiles += hm_cdiv(tk.count[t], kRows);
+    if (ntiles == 0) return 0;
+    switch (a.Xdim) {
+        case 1: return launch_fwd<1>(s, tk, a, Cb, info, ntiles, hyper, npass);
+        case 2: return launch_fwd<2>(s, tk, a, Cb, info, ntiles, hyper, npass);
+        case 3: return launch_fwd<3>(s, tk, a, Cb, info, ntiles, hyper, npass);
+        case 4: return launch_fwd<4>(s, tk, a, Cb, info, ntiles, hyper, npass);
+    }
+    hm_set_error("Xdim=%d unsupported", a.Xdim);
+    return HMOGP_ERR_ARG;
+}
