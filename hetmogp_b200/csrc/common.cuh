@@ -116,10 +116,10 @@ int hm_gram_tile(int prec);
 // ---------------------------------------------------------------- tensor-core path (tc_fwd.cu, tc_gram.cu)
 #define HM_GRAM_CHUNK 32                                   // data rows per Gram stage
 #define HM_GRAM_MAXV 6                                     // g-vectors per launch
-#define HM_GRAM_SLOT_DOUBLES (2 * 128 * 256 + HM_GRAM_MAXV * 128)
+#define HM_GRAM_SLOT_DOUBLES (128 * 256 + HM_GRAM_MAXV * 128)
 struct HmGramJob { int I, j0, nw; };                       // output tile: rows [128 I, 128 I + 128), columns [j0, j0 + nw)
 struct HmGramSeg { int q, I, j0, nw, chunk_begin, chunk_end, slot, has_g; };
-struct HmGramWeights {                                     // what one Gram launch accumulates
+struct HmGramWeights {                                     // what one Gram launch accumulates (nW == 1: one weight per launch)
     int nW, wbase[2], wdim[2];                             // H^k: weight = MW[wbase] (1 omega | 3 omega^c) * (wdim >= 0 ? s (x - z_row)[wdim] : 1)
     int nV, vbase[HM_GRAM_MAXV], vdim[HM_GRAM_MAXV];       // g^v: weight = MW[vbase] (0 mu | 2 mu^c) * (vdim >= 0 ? s (x - z_row)[vdim] : 1)
 };
@@ -129,6 +129,6 @@ int hm_tc_prepare(cudaStream_t s, const double* C, const HmConsts* consts, HmTcI
 int hm_tc_proj_fwd(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const void* Cb, const HmTcInfo* info, bool hyper,
                    int npass);
 int hm_tc_gram(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const HmTcInfo* info, const HmGramSeg* segs,
-               const int* seg_off, const HmGramWeights& gw, double* slots, int nctas, int flush_chunks, int npass);
+               const int* seg_off, const HmGramWeights& gw, double* slots, int nctas, int f1, int f2, int npass);
 int hm_tc_gram_reduce(cudaStream_t s, const double* slots, const HmGramJob* jobs, const int2* jobslots, int njobs, int Q,
-                      const HmGramWeights& gw, double* H0, double* H1, double* g0, int64_t gstride, int M, int Mp);
+                      const HmGramWeights& gw, double* H, double* g0, int64_t gstride, int M, int Mp);

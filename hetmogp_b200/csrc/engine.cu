@@ -390,7 +390,7 @@ struct hmogp_engine {
     // tensor-core path
     void* Cb;              // split-fp16 SW128 operand image of C
     HmTcInfo* tcinfo;
-    int tc_npass, tc_flush;
+    int tc_npass, tc_f1, tc_f2;   // MMA passes; level-1 window (chunks); level-3 period (windows)
     std::vector<HmGramJob> jobs_h;
     HmGramJob* jobs_d;
     HmGramSeg* segs_d; int* segoff_d; int2* jobslots_d;
@@ -568,7 +568,7 @@ int build_gram_plan(hmogp_engine* e) {
     std::vector<int2> jobslots((size_t)Q * nj);
     std::vector<int64_t> cost(nj);
     int64_t per_q = 0;
-    for (int j = 0; j < nj; ++j) { cost[j] = e->jobs_h[j].nw + 96; per_q += cost[j]; }
+    for (int j = 0; j < nj; ++j) { cost[j] = e->jobs_h[j].nw + 128; per_q += cost[j]; }   // generated columns per chunk (B + A)
     const double total = (double)per_q * (double)NC * Q;
     int slot = 0;
     double bs = 0.0;   // tape position of the current block
@@ -633,20 +633,18 @@ int tc_backward(hmogp_engine* e, int what, double* stats) {
     }
     HM_CUDA(cudaMemsetAsync(stats + e->off_H, 0, sizeof(double) * MM, s));
     if (nWt > 1) HM_CUDA(cudaMemsetAsync(e->Hx, 0, sizeof(double) * MM * (nWt - 1), s));
-    for (int w0 = 0; w0 < nWt; w0 += 2) {
+    for (int w0 = 0; w0 < nWt; ++w0) {
         HmGramWeights gw;
         memset(&gw, 0, sizeof(gw));
-        gw.nW = (nWt - w0) >= 2 ? 2 : 1;
-        for (int k = 0; k < gw.nW; ++k) { gw.wbase[k] = wb[w0 + k]; gw.wdim[k] = wd[w0 + k]; }
+        gw.nW = 1; gw.wbase[0] = wb[w0]; gw.wdim[0] = wd[w0]; gw.wdim[1] = -1;
         if (w0 == 0) {
             gw.vbase[gw.nV] = 0; gw.vdim[gw.nV++] = -1;                       // g^mu -> dVE/dm
             if (full)
                 for (int i = 0; i < Xd; ++i) { gw.vbase[gw.nV] = chain ? 2 : 0; gw.vdim[gw.nV++] = i; }   // sum_n mu^c s d_i K
         }
-        HM_CHECK(hm_tc_gram(s, e->tk, pa, e->tcinfo, e->segs_d, e->segoff_d, gw, e->slots, e->nworkers, e->tc_flush, e->tc_npass));
-        double* H0 = (w0 == 0) ? stats + e->off_H : e->Hx + (int64_t)(w0 - 1) * MM;
-        double* H1 = e->Hx + (int64_t)w0 * MM;
-        HM_CHECK(hm_tc_gram_reduce(s, e->slots, e->jobs_d, e->jobslots_d, (int)e->jobs_h.size(), Q, gw, H0, H1, e->gvec, gstride, M, Mp));
+        HM_CHECK(hm_tc_gram(s, e->tk, pa, e->tcinfo, e->segs_d, e->segoff_d, gw, e->slots, e->nworkers, e->tc_f1, e->tc_f2, e->tc_npass));
+        double* H = (w0 == 0) ? stats + e->off_H : e->Hx + (int64_t)(w0 - 1) * MM;
+        HM_CHECK(hm_tc_gram_reduce(s, e->slots, e->jobs_d, e->jobslots_d, (int)e->jobs_h.size(), Q, gw, H, e->gvec, gstride, M, Mp));
     }
     HM_CUDA(cudaMemcpyAsync(stats + e->off_g1, e->gvec, sizeof(double) * gstride, cudaMemcpyDeviceToDevice, s));
     if (full) {
@@ -765,9 +763,12 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
         const char* ev = getenv("HMOGP_TC_NPASS");
         e->tc_npass = ev ? atoi(ev) : 3;
         if (e->tc_npass < 1 || e->tc_npass > 3) e->tc_npass = 3;
-        ev = getenv("HMOGP_TC_FLUSH_ROWS");
-        e->tc_flush = (ev ? atoi(ev) : 4096) / HM_GRAM_CHUNK;
-        if (e->tc_flush < 1) e->tc_flush = 1;
+        ev = getenv("HMOGP_TC_FLUSH_ROWS");          // level-1 (tensor-core fp32) accumulation window
+        e->tc_f1 = (ev ? atoi(ev) : 512) / HM_GRAM_CHUNK;
+        if (e->tc_f1 < 1) e->tc_f1 = 1;
+        ev = getenv("HMOGP_TC_FLUSH3_ROWS");         // rows between fp64 flushes
+        e->tc_f2 = (ev ? atoi(ev) : 16384) / (e->tc_f1 * HM_GRAM_CHUNK);
+        if (e->tc_f2 < 1) e->tc_f2 = 1;
         unsigned short* cb = nullptr;
         rc = dalloc(e, &cb, hm_tc_image_elems(e->Mc, e->Q));
         e->Cb = cb;

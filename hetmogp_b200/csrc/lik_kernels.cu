@@ -48,7 +48,8 @@ struct HmLikRowArgs {
     double *rows_m, *rows_v, *rows_ve, *rows_dm, *rows_dv;
 };
 
-template <typename T>
+// KIND < 0: run-time likelihood dispatch (fp64 parity mode); KIND >= 0: fp32 kernel specialised on the likelihood
+template <typename T, int KIND, int D>
 __global__ void __launch_bounds__(HM_LIK_THREADS) lik_rows_kernel(HmLikRowArgs p) {
     __shared__ double sacc[HM_LIK_THREADS / 32][HM_LIK_MAXSTAT];
     const int nbase = 2 + p.dimf * (1 + 2 * p.Q);
@@ -82,7 +83,8 @@ __global__ void __launch_bounds__(HM_LIK_THREADS) lik_rows_kernel(HmLikRowArgs p
         }
         const T y = T(p.Y[p.begin + row]);
         HmLikOut<T> o;
-        hm_lik_eval<T>(p.kind, p.K, T(p.sigma), y, m, v, o);
+        if constexpr (KIND >= 0) hm_lik_eval_f32<KIND, D>(p.K, (float)p.sigma, y, m, v, p.want_grads != 0 || p.rows_m != nullptr, o);
+        else hm_lik_eval<T>(p.kind, p.K, T(p.sigma), y, m, v, o);
         o.ve *= bs;
         for (int f = 0; f < F; ++f) { o.dm[f] *= bs; o.dv[f] *= bs; }
         st[0] += (double)o.ve;
@@ -170,8 +172,29 @@ int hm_lik_rows(cudaStream_t s, int prec, const HmTasks& tk, const HmConsts* con
     if (nb > max_blocks) nb = max_blocks;
     if (nb < 1) nb = 1;
     *nblocks_out = (int)nb;
-    if (prec == HMOGP_PREC_FP64) lik_rows_kernel<double><<<(unsigned)nb, HM_LIK_THREADS, 0, s>>>(p);
-    else lik_rows_kernel<float><<<(unsigned)nb, HM_LIK_THREADS, 0, s>>>(p);
+    if (prec == HMOGP_PREC_FP64) lik_rows_kernel<double, -1, 0><<<(unsigned)nb, HM_LIK_THREADS, 0, s>>>(p);
+    else {
+#define HM_LIK_LAUNCH(KIND_, D_) lik_rows_kernel<float, KIND_, D_><<<(unsigned)nb, HM_LIK_THREADS, 0, s>>>(p)
+        switch (p.kind) {
+            case HMOGP_LIK_GAUSSIAN: HM_LIK_LAUNCH(HMOGP_LIK_GAUSSIAN, 0); break;
+            case HMOGP_LIK_HETGAUSSIAN: HM_LIK_LAUNCH(HMOGP_LIK_HETGAUSSIAN, 0); break;
+            case HMOGP_LIK_BERNOULLI: HM_LIK_LAUNCH(HMOGP_LIK_BERNOULLI, 0); break;
+            case HMOGP_LIK_POISSON: HM_LIK_LAUNCH(HMOGP_LIK_POISSON, 0); break;
+            case HMOGP_LIK_EXPONENTIAL: HM_LIK_LAUNCH(HMOGP_LIK_EXPONENTIAL, 0); break;
+            case HMOGP_LIK_GAMMA: HM_LIK_LAUNCH(HMOGP_LIK_GAMMA, 0); break;
+            case HMOGP_LIK_BETA: HM_LIK_LAUNCH(HMOGP_LIK_BETA, 0); break;
+            case HMOGP_LIK_CATEGORICAL:
+                switch (p.dimf) {
+                    case 1: HM_LIK_LAUNCH(HMOGP_LIK_CATEGORICAL, 1); break;
+                    case 2: HM_LIK_LAUNCH(HMOGP_LIK_CATEGORICAL, 2); break;
+                    case 3: HM_LIK_LAUNCH(HMOGP_LIK_CATEGORICAL, 3); break;
+                    default: HM_LIK_LAUNCH(HMOGP_LIK_CATEGORICAL, 4); break;
+                }
+                break;
+            default: hm_set_error("unknown likelihood kind %d", p.kind); return HMOGP_ERR_ARG;
+        }
+#undef HM_LIK_LAUNCH
+    }
     HM_CUDA(cudaGetLastError());
     return 0;
 }

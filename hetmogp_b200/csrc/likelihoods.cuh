@@ -234,3 +234,182 @@ __device__ void hm_lik_eval(int kind, int K, T sigma, T y, const T* m, const T* 
         o.dv[1] = half * d2b * inv_pi;
     }
 }
+
+// ================================================================== fp32 fast paths (tensor-core / fp32 engines)
+// Same expectations as hm_lik_eval<float>, restructured for throughput; each one states why it is equivalent.
+__device__ __forceinline__ float hm_rcp(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float hm_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// lgamma, digamma and trigamma of x > 0 in one pass: a predicated 6-step upward recurrence shared by the three
+// (product for lgamma, sum 1/x for psi, sum 1/x^2 for zeta(2,.)), then the Stirling / asymptotic series at x >= 6.
+__device__ __forceinline__ void hm_lgam_psi_tri(float x, float& lg, float& ps, float& tr) {
+    float rec = 0.f, rec2 = 0.f, prod = 1.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        if (x < 6.f) {
+            const float r = hm_rcp(x);
+            rec += r;
+            rec2 = fmaf(r, r, rec2);
+            prod *= x;
+            x += 1.f;
+        }
+    }
+    const float xi = hm_rcp(x), x2 = xi * xi;
+    const float lx = 0.6931471805599453f * hm_lg2(x);
+    lg = fmaf(x - 0.5f, lx, -x) + 0.9189385332046727f +
+         xi * (0.08333333333333333f - x2 * (0.002777777777777778f - x2 * (7.936507936507937e-4f - x2 * 5.952380952380953e-4f))) -
+         0.6931471805599453f * hm_lg2(prod);
+    ps = lx - 0.5f * xi -
+         x2 * (0.08333333333333333f - x2 * (0.008333333333333333f - x2 * (0.003968253968253968f - x2 * (0.004166666666666667f - x2 * 0.007575757575757576f)))) -
+         rec;
+    tr = xi * (1.f + 0.5f * xi +
+               x2 * (0.16666666666666666f - x2 * (0.03333333333333333f - x2 * (0.023809523809523808f - x2 * (0.03333333333333333f - x2 * 0.07575757575757576f))))) +
+         rec2;
+}
+
+// Categorical, D = K - 1 latent functions on a 10^D tensor grid (categorical.py:130-222).
+// With den = 1 + sum_d e^{f_d}:  p_d = e^{f_d}/den, p_K = 1/den.  When no probability on the whole grid reaches the
+// reference's clip [1e-9, 1-1e-9] (checked per row from the extreme nodes), the clip and the renormalisation
+// p / p.sum() are the identity up to round-off, so
+//     log p_y = f_y - log den (y <= D) | -log den (y = K),   E[f_y] = m_y exactly (sum w = 1, sum w x = 0),
+//     E[log p_y] = m_y [y <= D] - sum_g w_g log den_g,       d2logp_df2_d = -rho_d (1 - rho_d), rho_d = e^{f_d}/den.
+// Rows where a clip could be active take the literal path (hm_lik_eval<float>).
+template <int D>
+__device__ __forceinline__ void hm_categorical_fast(int K, float y, const float* m, const float* v, bool want_grads,
+                                                    HmLikOut<float>& o) {
+    static_assert(D >= 1 && D <= HM_MAXF, "categorical fast path: 1..4 latent functions");
+    float e[D][10], emax[D], emin[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const float s2v = sqrtf(2.f * v[d]);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) e[d][i] = hm_safe_exp((float)c_gh10_x[i] * s2v + m[d]);
+        emax[d] = fmaxf(e[d][0], e[d][9]);
+        emin[d] = fminf(e[d][0], e[d][9]);
+    }
+    float den_max = 1.f, pmin = 1.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { den_max += emax[d]; pmin = fminf(pmin, emin[d]); }
+    const bool finite_ok = den_max < 1.0e30f && !(v[0] != v[0]);
+    bool no_clip = finite_ok && (pmin >= 1.0e-9f * den_max) && (den_max <= 1.0e9f);   // min p >= 1e-9 over the grid
+#pragma unroll
+    for (int d = 0; d < D; ++d) no_clip = no_clip && (v[d] >= 0.f);
+    if (!no_clip) { hm_lik_eval<float>(HMOGP_LIK_CATEGORICAL, K, 0.f, y, m, v, o); return; }
+    const int label = (int)y;
+    const bool valid = ((float)label == y) && label >= 1 && label <= K;
+    float w10[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) w10[i] = (float)c_gh10_w[i];
+    // nested loops, last function fastest (C-order of categorical.py:153-157; the sums do not depend on the order)
+    float S = 0.f, t[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) t[d] = 0.f;
+    constexpr int NOUT = (D == 1) ? 1 : (D == 2 ? 10 : (D == 3 ? 100 : 1000));
+    for (int g = 0; g < NOUT; ++g) {
+        // outer axes 0..D-2 (dynamic), inner axis D-1 unrolled
+        float base = 1.f, wo = 1.f, eo[D > 1 ? D - 1 : 1];
+        int r = g;
+#pragma unroll
+        for (int d = D - 2; d >= 0; --d) {
+            const int idx = r % 10; r /= 10;
+            float ev = e[d][0], wv = w10[0];
+#pragma unroll
+            for (int i = 1; i < 10; ++i) { ev = (idx == i) ? e[d][i] : ev; wv = (idx == i) ? w10[i] : wv; }
+            eo[d] = ev; base += ev; wo *= wv;
+        }
+        float s_in = 0.f, t_in[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) t_in[d] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            const float den = base + e[D - 1][k];
+            s_in = fmaf(w10[k], hm_lg2(den), s_in);
+            if (want_grads) {
+                const float inv = hm_rcp(den);
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const float rho = ((d == D - 1) ? e[D - 1][k] : eo[d < D - 1 ? d : 0]) * inv;
+                    t_in[d] = fmaf(w10[k], fmaf(-rho, rho, rho), t_in[d]);
+                }
+            }
+        }
+        S = fmaf(wo, s_in, S);
+#pragma unroll
+        for (int d = 0; d < D; ++d) t[d] = fmaf(wo, t_in[d], t[d]);
+    }
+    const float ve = ((label >= 1 && label <= D) ? m[label - 1] : 0.f) - 0.6931471805599453f * S;
+    o.ve = valid ? ve : -CUDART_INF_F;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        o.dm[d] = valid ? ((label == d + 1 ? 1.f : 0.f) - 1.f) : 0.f;   // quirk C-1 (weights sum to 1)
+        o.dv[d] = valid ? -0.5f * t[d] : 0.f;
+    }
+}
+
+// Gamma / Beta on the 10 x 10 grid (gamma.py:103-194, beta.py:106-197), special functions through hm_lgam_psi_tri.
+template <bool IS_GAMMA>
+__device__ __forceinline__ void hm_gamma_beta_fast(float y, const float* m, const float* v, HmLikOut<float>& o) {
+    const float inv_pi = 0.31830988618379067f;   // quirk C-2
+    const float sa = sqrtf(2.f * v[0]), sb = sqrtf(2.f * v[1]);
+    float a[10], b[10], lga[10], psa[10], tra[10], lgb[10], psb[10], trb[10], w10[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        w10[i] = (float)c_gh10_w[i];
+        a[i] = hm_clip(hm_safe_exp((float)c_gh10_x[i] * sa + m[0]), 1e-9f, 1e9f);
+        b[i] = hm_clip(hm_safe_exp((float)c_gh10_x[i] * sb + m[1]), 1e-9f, 1e9f);
+        hm_lgam_psi_tri(a[i], lga[i], psa[i], tra[i]);
+        if (IS_GAMMA) { lgb[i] = logf(b[i]); psb[i] = 0.f; trb[i] = 0.f; }
+        else hm_lgam_psi_tri(b[i], lgb[i], psb[i], trb[i]);
+    }
+    const float logy = logf(y), log1y = IS_GAMMA ? 0.f : logf(1.f - y);
+    float ve = 0.f, da = 0.f, db = 0.f, d2a = 0.f, d2b = 0.f;
+    if (IS_GAMMA) {
+        // every term is separable in (i, j): with sum_j w_j = W1, sum_j w_j log b_j = LB, sum_j w_j b_j = B1
+        float W1 = 0.f, LB = 0.f, B1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) { W1 += w10[j]; LB = fmaf(w10[j], lgb[j], LB); B1 = fmaf(w10[j], b[j], B1); }
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const float wi = w10[i], ai = a[i];
+            ve = fmaf(wi, (-lga[i] + (ai - 1.f) * logy) * W1 + ai * LB - y * B1, ve);
+            da = fmaf(wi, ((-psa[i] + logy) * W1 + LB) * ai, da);
+            db = fmaf(wi, ai * W1 - y * B1, db);
+            d2a = fmaf(wi, ((-psa[i] - ai * tra[i] + logy) * W1 + LB) * ai, d2a);
+            d2b = fmaf(wi, -y * B1, d2b);
+        }
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < 10; ++i) {
+            float rve = 0.f, rda = 0.f, rdb = 0.f, r2a = 0.f, r2b = 0.f;
+            const float ai = a[i];
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                float lgab, psab, trab;
+                hm_lgam_psi_tri(ai + b[j], lgab, psab, trab);
+                const float wj = w10[j], bj = b[j];
+                rve = fmaf(wj, (ai - 1.f) * logy + (bj - 1.f) * log1y - (lga[i] + lgb[j] - lgab), rve);
+                rda = fmaf(wj, (psab - psa[i] + logy) * ai, rda);
+                rdb = fmaf(wj, (psab - psb[j] + log1y) * bj, rdb);
+                r2a = fmaf(wj, (psab + ai * trab - psa[i] - ai * tra[i] + logy) * ai, r2a);
+                r2b = fmaf(wj, (psab + bj * trab - psb[j] - bj * trb[j] + log1y) * bj, r2b);
+            }
+            ve = fmaf(w10[i], rve, ve); da = fmaf(w10[i], rda, da); db = fmaf(w10[i], rdb, db);
+            d2a = fmaf(w10[i], r2a, d2a); d2b = fmaf(w10[i], r2b, d2b);
+        }
+    }
+    o.ve = ve * inv_pi;
+    o.dm[0] = da * inv_pi;
+    o.dm[1] = db * inv_pi;
+    o.dv[0] = 0.5f * d2a * inv_pi;
+    o.dv[1] = 0.5f * d2b * inv_pi;
+}
+
+// compile-time dispatch used by the fp32 row kernel (KIND = likelihood kind, D = Categorical latent functions)
+template <int KIND, int D>
+__device__ __forceinline__ void hm_lik_eval_f32(int K, float sigma, float y, const float* m, const float* v, bool want_grads,
+                                                HmLikOut<float>& o) {
+    if constexpr (KIND == HMOGP_LIK_CATEGORICAL) hm_categorical_fast<D>(K, y, m, v, want_grads, o);
+    else if constexpr (KIND == HMOGP_LIK_GAMMA) hm_gamma_beta_fast<true>(y, m, v, o);
+    else if constexpr (KIND == HMOGP_LIK_BETA) hm_gamma_beta_fast<false>(y, m, v, o);
+    else hm_lik_eval<float>(KIND, K, sigma, y, m, v, o);
+}

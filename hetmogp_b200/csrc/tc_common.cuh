@@ -41,9 +41,14 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a protocol bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try(bar, parity)) {
-        if (clock64() - t0 > 8000000000LL) __trap();   // ~4 s at 2 GHz
+    long long t0 = 0;
+    for (uint32_t it = 1;; ++it) {
+        if (mbar_try(bar, parity)) return;
+        if ((it & 1023u) == 0) {                       // sleeping waiters wake on every barrier event: keep the loop lean
+            const long long t = clock64();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 8000000000LL) __trap();  // ~4 s at 2 GHz
+        }
     }
 }
 // Warp-collective wait: every lane executes the (hardware-suspended) try_wait, so the warp stays converged.
@@ -99,6 +104,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// one row (lane) per thread: 32 consecutive fp32 columns registers -> TMEM
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30)
 // (unused for swizzled K-major, 1), SBO>>4 [32,46) = bytes between 8-row groups, version 1 [46,48), layout [61,64).
