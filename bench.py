@@ -85,11 +85,15 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def algorithmic_work(N_tasks, M, Q, Xdim):
-    """U = (sum_t Q N_t) M^2; full step (4+Xdim) U flops; irreducible HBM bytes sum_t N_t (Xdim+1) 8."""
+def algorithmic_work(N_tasks, M, Q, Xdim, what="full"):
+    """U = (sum_t Q N_t) M^2 multiply-adds.  Forward quadratic form 2U flops; every weighted Gram of
+    the backward pass is symmetric-aware U flops: one (H^1) in a VE step, 1 + Xdim (H^1 and the distance-weighted
+    D^i) in a full step  =>  full step (3 + Xdim) U on the Gram formulation (the SIMT path recomputes the projection
+    instead: (4 + Xdim) U).  Irreducible HBM bytes: sum_t N_t (Xdim + 1) 8."""
     P = sum(Q * n for n in N_tasks)
     U = float(P) * M * M
-    return dict(U=U, flops_full=(4 + Xdim) * U, flops_fwd=2 * U, flops_bwd_proj=2 * U, flops_gram=U,
+    n_gram = {"elbo": 0, "ve": 1, "full": 1 + Xdim}[what]
+    return dict(U=U, flops_full=(2 + n_gram) * U, flops_fwd=2 * U, flops_bwd_proj=2 * U, flops_gram=U, n_gram=n_gram,
                 bytes=float(sum(N_tasks)) * (Xdim + 1) * 8)
 
 
@@ -260,18 +264,38 @@ def main():
 
     # ---------------------------------------------------------------- roofline of the dominant kernel (live CUDA-event times)
     peaks = load_peaks()
-    work = algorithmic_work(count, M, Q, Xdim)   # this rank's shard
+    work = algorithmic_work(count, M, Q, Xdim, args.what)   # this rank's shard
     med = {k: float(np.median([p[k] for p in phases])) for k in phases[0] if k.endswith("_ms")}
-    kern = {"forward_ms": ("proj_fwd (K_fu build + projection)", work["flops_fwd"]),
-            "bwd_proj_ms": ("proj_bwd (K_fu rebuild + projection + hyper column stats)", work["flops_bwd_proj"]),
-            "bwd_gram_ms": ("gram (K_fu^T diag(w) K_fu)", work["flops_gram"])}
-    dom = max(kern, key=lambda k: med.get(k, 0.0))
-    ach = kern[dom][1] / (med[dom] * 1e-3) / 1e12 if med.get(dom, 0) > 0 else 0.0
-    n_kernel_ms = sum(med[k] for k in kern)
+    # (kernel name, algorithmic flops per launch, launches per step) of the N-sized kernels behind each phase timer
+    if prec == "tc":
+        kern = {"forward_ms": ("tc_fwd_kernel (K_fu build + K_fu C_q on tcgen05 + row reductions)", work["flops_fwd"], 1),
+                "bwd_gram_ms": ("tc_gram_kernel (K_fu^T diag(w) K_fu on tcgen05, one launch per weight)", work["flops_gram"],
+                                max(1, work["n_gram"]))}
+    else:
+        kern = {"forward_ms": ("proj_fwd (K_fu build + projection)", work["flops_fwd"], 1),
+                "bwd_proj_ms": ("proj_bwd (K_fu rebuild + projection + hyper column stats)", work["flops_bwd_proj"], 1),
+                "bwd_gram_ms": ("gram (K_fu^T diag(w) K_fu)", work["flops_gram"], 1)}
+    per_launch = {k: med.get(k, 0.0) / kern[k][2] for k in kern}
+    dom = max(kern, key=lambda k: per_launch[k])
+    ach = kern[dom][1] / (per_launch[dom] * 1e-3) / 1e12 if per_launch[dom] > 0 else 0.0
+    n_kernel_ms = sum(med.get(k, 0.0) for k in kern)
+    Mc = -(-M // 256) * 256
+    issued = {"forward_ms": 3 * 2.0 * work["U"] / (M * M) * Mc * Mc,                       # 3 split-fp16 products, padded M
+              "bwd_gram_ms": 3 * 2.0 * work["U"] / (M * M) * (Mc * Mc) * 0.625}            # lower block-triangle of 128x256 tiles
+    traffic = {"tc_gram_kernel": 1.85e9, "tc_fwd_kernel": 4.3e8}   # dram read+write per launch, ncu --set full (profiles/r1_tc_*)
     roofline = {"bound": "tensor", "kernel": kern[dom][0], "achieved": ach, "peak": peaks["tc"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tc"], "traffic": None, "peak_source": peaks["src"] + " bf16 sustained (kernel timed inside a long step)",
-                "operand_format": {"tc": "split-bf16 (3 products) on tcgen05", "fp32": "fp32 FFMA (CUDA cores)", "fp64": "fp64 DFMA"}[prec],
-                "algorithmic_flops_per_launch": kern[dom][1], "ms_per_launch": med[dom],
+                "frac": ach / peaks["tc"],
+                "traffic": (traffic["tc_gram_kernel"] if dom == "bwd_gram_ms" else traffic["tc_fwd_kernel"]) if (prec == "tc" and args.config == "cfg3" and world == 1 and not args.rows) else None,
+                "peak_source": peaks["src"] + " bf16 sustained (kernel timed inside a long step)",
+                "operand_format": {"tc": "split-fp16 hi/lo, 3 tcgen05.mma products per algorithmic product (fp32-class accuracy); "
+                                         "the algorithmic fraction is therefore bounded by 1/3 of the bf16 peak",
+                                   "fp32": "fp32 FFMA (CUDA cores)", "fp64": "fp64 DFMA"}[prec],
+                "algorithmic_flops_per_launch": kern[dom][1], "ms_per_launch": per_launch[dom], "launches_per_step": kern[dom][2],
+                "issued_mma_tflops": ({k: issued[k] * (kern[k][2] if k == "bwd_gram_ms" else 1) / (med[k] * 1e-3) / 1e12
+                                       for k in kern if med.get(k, 0) > 0} if prec == "tc" else None),
+                "all_kernels": {kern[k][0].split(" ")[0]: {"ms_per_launch": per_launch[k], "launches": kern[k][2],
+                                                            "achieved_TFLOPs": kern[k][1] / (per_launch[k] * 1e-3) / 1e12 if per_launch[k] > 0 else 0.0}
+                                for k in kern},
                 "step_algorithmic_tflops": work["flops_full"] / (ms_step * 1e-3) / 1e12,
                 "hbm_view": {"achieved_GBps": work["bytes"] / (n_kernel_ms * 1e-3) / 1e9, "peak_GBps": peaks["hbm"],
                              "frac": work["bytes"] / (n_kernel_ms * 1e-3) / 1e9 / peaks["hbm"],
@@ -282,7 +306,7 @@ def main():
         cpu = cpu_baseline(args.config, args.cpu_rows, steps=1)
     line = {"metric": "ELBO steps/sec (ELBO + all gradients)", "value": 1e3 / ms_step, "unit": "ELBO steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": {"tc": "bf16x3", "fp32": "f32", "fp64": "f64"}[prec],
+            "scaling": "strong", "vs_baseline": None, "dtype": {"tc": "f16x3 (split fp16 on tcgen05, fp32 accumulate; fp64 M x M algebra)", "fp32": "f32", "fp64": "f64"}[prec],
             "data": "synthetic", "config": workload_config(args, c), "elbo": elbo_resident, "clocks": clocks,
             "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": wall}
     print(json.dumps(line))

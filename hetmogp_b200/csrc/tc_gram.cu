@@ -191,7 +191,7 @@ tc_gram_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, con
                 for (int c = c0; c < c1; ++c, ++cc_) {
                     const int stage = cc_ % kGStages, rs = cc_ % kRowSlots;
                     if (pend.on) {   // fold the previous window as soon as its MMAs are done, or before we would block on them
-                        if (mbar_try(&sb->accfull, pend.parity) || !mbar_try(&sb->empty[stage], ((cc_ / kGStages) & 1u) ^ 1u)) {
+                        if (mbar_test(&sb->accfull, pend.parity) || !mbar_test(&sb->empty[stage], ((cc_ / kGStages) & 1u) ^ 1u)) {
                             flush_window(pend);
                             pend.on = false;
                         }

@@ -24,7 +24,7 @@ if __name__ == "__main__":
     for name in names:
         c = dict(CASES[name])
         prob = synth.make_problem(c.pop("liks"), c.pop("N"), c.pop("M"), c.pop("Q"), Xdim=c.pop("Xdim"), seed=7, **c)
-        for prec in ("fp64", "fp32"):
+        for prec in ("fp64", "fp32", "tc"):
             t0 = time.time()
             try:
                 err, out, o = pu.compare(prob, prec)

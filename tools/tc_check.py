@@ -74,8 +74,27 @@ def scale(cfg, N, ref_prec="fp64", whats=("full",)):
               "  ".join("%s=%.2e" % (k, pu.relerr(o32[k], o[k])) for k in GRADS))
 
 
+def determinism(cfg, N):
+    """Bit-reproducibility of repeated evaluations and of the ELBO across what-levels."""
+    prob = synth.make_config(cfg, N=N)
+    p = pu.params_of(prob)
+    eng = pu.make_engine(prob, "tc")
+    vals = {}
+    for what in ("full", "full", "ve", "ve", "elbo", "elbo", "full"):
+        o = eng.evaluate(p, what=what)
+        vals.setdefault(what, []).append((repr(float(o["log_marginal"][0, 0])), [repr(float(v)) for v in o["VE"]],
+                                          None if what == "elbo" else float(np.abs(o["dL_dL_u"]).sum())))
+    for k, v in vals.items():
+        for x in v:
+            print("DET", k, x)
+    eng.close()
+
+
 if __name__ == "__main__":
     mode = sys.argv[1]
+    if mode == "det":
+        determinism(sys.argv[2], int(sys.argv[3]))
+        sys.exit(0)
     if mode == "small":
         small(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "tc")
     elif mode == "scale":
