@@ -282,7 +282,7 @@ def main():
     Mc = -(-M // 256) * 256
     issued = {"forward_ms": 3 * 2.0 * work["U"] / (M * M) * Mc * Mc,                       # 3 split-fp16 products, padded M
               "bwd_gram_ms": 3 * 2.0 * work["U"] / (M * M) * (Mc * Mc) * 0.625}            # lower block-triangle of 128x256 tiles
-    traffic = {"tc_gram_kernel": 1.85e9, "tc_fwd_kernel": 4.3e8}   # dram read+write per launch, ncu --set full (profiles/r1_tc_*)
+    traffic = {"tc_gram_kernel": 1.03e9, "tc_fwd_kernel": 3.1e8}   # dram read+write per launch, ncu --set full (profiles/r1_tc_ncu_summary.txt)
     roofline = {"bound": "tensor", "kernel": kern[dom][0], "achieved": ach, "peak": peaks["tc"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tc"],
                 "traffic": (traffic["tc_gram_kernel"] if dom == "bwd_gram_ms" else traffic["tc_fwd_kernel"]) if (prec == "tc" and args.config == "cfg3" and world == 1 and not args.rows) else None,

@@ -61,9 +61,12 @@ struct HmTasks {
     const double* Y[HM_MAXT];  // [N_t]
     int64_t begin[HM_MAXT];    // active slice
     int64_t count[HM_MAXT];
-    void* AC[HM_MAXT];         // [count, acs] a_tq, c_tq (+ b_tq, e_tq on the tensor-core path)  (compute type)
-    void* MW[HM_MAXT];         // [count, 4Q]  mu, omega, mu_c, omega_c (compute type)
-    int acs;                   // AC row stride in elements: 2Q (SIMT) or 4Q (tensor-core path)
+    // per-row intermediates, structure-of-arrays so that every pass streams full sectors:  array k of task t starts at
+    // base + k * cap[t], row r of the active slice at [r]
+    void* AC[HM_MAXT];         // [acs][cap]  k = Q*0+q: a_tq, Q*1+q: c_tq (+ Q*2+q: b_tq, Q*3+q: e_tq on the tensor-core path)
+    void* MW[HM_MAXT];         // [4Q][cap]   k = Q*0+q: mu, Q*1+q: omega, Q*2+q: mu_c, Q*3+q: omega_c
+    int64_t cap[HM_MAXT];      // allocated rows per array
+    int acs;                   // arrays in AC: 2Q (SIMT) or 4Q (tensor-core path)
 };
 
 // Per-step scale state of the tensor-core path (device resident; see tc_common.cuh "split fp16").
@@ -71,6 +74,7 @@ struct HmTcInfo {
     int cexp[HM_MAXQ];             // C_q is carried as C_q * 2^cexp   (|.| < 2^14)
     int kexp[HM_MAXQ];             // K_tq is carried as K_tq * 2^kexp (sigma_q^2 -> [2^11, 2^12))
     unsigned wmax[2][HM_MAXQ];     // float bits of max_n |omega_tq|, max_n |omega^c_tq| (likelihood kernel, atomicMax)
+    unsigned cmax[HM_MAXQ];        // float bits of max |C_q|
 };
 
 // ---------------------------------------------------------------- M x M fp64 algebra (mm_algebra.cu)
@@ -116,7 +120,8 @@ int hm_gram_tile(int prec);
 // ---------------------------------------------------------------- tensor-core path (tc_fwd.cu, tc_gram.cu)
 #define HM_GRAM_CHUNK 32                                   // data rows per Gram stage
 #define HM_GRAM_MAXV 6                                     // g-vectors per launch
-#define HM_GRAM_SLOT_DOUBLES (128 * 256 + HM_GRAM_MAXV * 128)
+#define HM_GRAM_ROWSPLIT 2                                 // generator warps per column group (partial g-vectors per slot)
+#define HM_GRAM_SLOT_DOUBLES (128 * 256 + HM_GRAM_ROWSPLIT * HM_GRAM_MAXV * 128)
 struct HmGramJob { int I, j0, nw; };                       // output tile: rows [128 I, 128 I + 128), columns [j0, j0 + nw)
 struct HmGramSeg { int q, I, j0, nw, chunk_begin, chunk_end, slot, has_g; };
 struct HmGramWeights {                                     // what one Gram launch accumulates (nW == 1: one weight per launch)

@@ -95,36 +95,42 @@ __global__ void make_c_kernel(const double* KSK, const double* Ki, double* C, fl
 }
 
 // KL_q = 0.5 sum(Ki o S) + 0.5 m.alpha - 0.5 M + sum log|diag Luu| - sum log|diag Lu|   (svmogp_inf.py:243-250)
-// also flags inf in S^-1 (svmogp_inf.py:126).  One block per q.
+// also flags inf in S^-1 (svmogp_inf.py:126).  grid = (row blocks, Q): per-block partials in KLpart[q][block]
+// (summed in a fixed order by kl_finish_kernel -> deterministic).
 __global__ void kl_kernel(const double* Ki, const double* S, const double* Sinv, const double* mp, const double* alpha,
-                          const double* Luu, const double* Lu, double* KLq, int* lu_singular, int M, int Mp) {
-    const int q = blockIdx.x;
+                          const double* Luu, const double* Lu, double* KLpart, int* lu_singular, int M, int Mp) {
+    const int q = blockIdx.y;
     const int64_t base = (int64_t)q * Mp * Mp;
     double s = 0.0;
     int bad = 0;
-    for (int64_t e = threadIdx.x; e < (int64_t)M * M; e += blockDim.x) {
-        const int i = (int)(e / M), j = (int)(e % M);
-        s += 0.5 * Ki[base + (int64_t)i * Mp + j] * S[base + (int64_t)i * Mp + j];
-        if (isinf(Sinv[base + (int64_t)i * Mp + j])) bad = 1;
-    }
-    for (int i = threadIdx.x; i < M; i += blockDim.x) {
-        s += 0.5 * mp[(int64_t)q * Mp + i] * alpha[(int64_t)q * Mp + i];
-        s += log(fabs(Luu[base + (int64_t)i * Mp + i])) - log(fabs(Lu[base + (int64_t)i * Mp + i]));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int i = blockIdx.x * nwarp + warp; i < M; i += gridDim.x * nwarp) {
+        const int64_t ro = base + (int64_t)i * Mp;
+        for (int j = lane; j < M; j += 32) {
+            s += 0.5 * Ki[ro + j] * S[ro + j];
+            if (isinf(Sinv[ro + j])) bad = 1;
+        }
+        if (lane == 0) {
+            s += 0.5 * mp[(int64_t)q * Mp + i] * alpha[(int64_t)q * Mp + i];
+            s += log(fabs(Luu[ro + i])) - log(fabs(Lu[ro + i]));
+        }
     }
     __shared__ double sh[32];
-    __shared__ int shbad;
-    if (threadIdx.x == 0) shbad = 0;
-    __syncthreads();
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x / 32] = s;
-    if (bad) atomicOr(&shbad, 1);
+    if (lane == 0) sh[warp] = s;
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&lu_singular[q], 1);
     __syncthreads();
     if (threadIdx.x == 0) {
         double tot = 0.0;
-        for (int w = 0; w < (int)blockDim.x / 32; ++w) tot += sh[w];
-        KLq[q] = tot - 0.5 * M;
-        lu_singular[q] = shbad;
+        for (int w = 0; w < nwarp; ++w) tot += sh[w];
+        KLpart[q * gridDim.x + blockIdx.x] = tot;
     }
+}
+__global__ void kl_finish_kernel(const double* KLpart, int nblk, double* KLq, int M) {
+    const int q = threadIdx.x;
+    double tot = 0.0;
+    for (int b = 0; b < nblk; ++b) tot += KLpart[q * nblk + b];
+    KLq[q] = tot - 0.5 * M;
 }
 
 // ---- statistic reducers (deterministic: fixed summation order)
@@ -399,7 +405,9 @@ struct hmogp_engine {
     double* Hx;            // [1 + Xd][Q][Mp][Mp] extra Grams
     double* gvec;          // [HM_GRAM_MAXV][Q][Mp]
     bool plan_dirty;
-    double *KLq, *jitter_d, *rowstat, *dzmm;
+    double *KLq, *KLpart, *jitter_d, *rowstat, *dzmm;
+    cudaStream_t s2;          // side stream of the prepare phase (S, S^-1 branch)
+    cudaEvent_t ev_fork, ev_S, ev_Sinv;
     int *flags_d;  // [2][HM_MAXQ]: chol_fail, lu_singular
     // statistics
     int64_t stats_len;
@@ -495,6 +503,15 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
         pad_inputs_kernel<<<grid, 128, 0, s>>>(e->pZ, e->pm, e->pL, e->Zp, e->mp, e->Lu, M, Mp, Q, Xd);
         HM_CUDA(cudaGetLastError());
     }
+    // ---- side stream: S = Lu Lu^T (svmogp_inf.py:193-195) and S^-1 (svmogp_inf.py:124) do not depend on K_uu
+    cudaStream_t s2 = e->s2;
+    HM_CUDA(cudaEventRecord(e->ev_fork, s));
+    HM_CUDA(cudaStreamWaitEvent(s2, e->ev_fork, 0));
+    HM_CHECK(hm_dgemm(s2, false, true, Mp, Mp, Mp, 1.0, e->Lu, Mp, sQ, e->Lu, Mp, sQ, 0.0, e->S, Mp, sQ, Q));
+    HM_CUDA(cudaEventRecord(e->ev_S, s2));
+    HM_CHECK(hm_tri_inverse(s2, e->Lu, e->LuInv, e->T1, Mp, sQ, Q));
+    HM_CHECK(hm_dgemm(s2, true, false, Mp, Mp, Mp, 1.0, e->LuInv, Mp, sQ, e->LuInv, Mp, sQ, 0.0, e->Sinv, Mp, sQ, Q));
+    HM_CUDA(cudaEventRecord(e->ev_Sinv, s2));
     // K_uu, jitchol (util.py:197-198): no jitter unless the plain factorisation fails; then var*1e-6 * 10^k, k<5
     double var_h[HM_MAXQ];
     bool have_var = false;
@@ -511,7 +528,11 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
         bool any = false;
         for (int q = 0; q < Q; ++q) any = any || fl[q];
         if (!any) break;
-        if (attempt >= 5) { hm_set_error("not positive definite, even with jitter."); return HMOGP_ERR_LINALG; }
+        if (attempt >= 5) {
+            cudaStreamSynchronize(s2);
+            hm_set_error("not positive definite, even with jitter.");
+            return HMOGP_ERR_LINALG;
+        }
         if (!have_var) {
             HM_CUDA(cudaMemcpy(var_h, e->pvar, sizeof(double) * Q, cudaMemcpyDeviceToHost));
             have_var = true;
@@ -522,16 +543,13 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
     // K_uu^-1 = Luu^-T Luu^-1   (dpotri, util.py:199)
     HM_CHECK(hm_tri_inverse(s, e->Luu, e->LuuInv, e->tmp, Mp, sQ, Q));
     HM_CHECK(hm_dgemm(s, true, false, Mp, Mp, Mp, 1.0, e->LuuInv, Mp, sQ, e->LuuInv, Mp, sQ, 0.0, e->Ki, Mp, sQ, Q));
-    // S = Lu Lu^T (svmogp_inf.py:193-195); S^-1 (svmogp_inf.py:124)
-    HM_CHECK(hm_dgemm(s, false, true, Mp, Mp, Mp, 1.0, e->Lu, Mp, sQ, e->Lu, Mp, sQ, 0.0, e->S, Mp, sQ, Q));
-    HM_CHECK(hm_tri_inverse(s, e->Lu, e->LuInv, e->tmp, Mp, sQ, Q));
-    HM_CHECK(hm_dgemm(s, true, false, Mp, Mp, Mp, 1.0, e->LuInv, Mp, sQ, e->LuInv, Mp, sQ, 0.0, e->Sinv, Mp, sQ, Q));
     // alpha = Ki m ; SK = S Ki ; KSK = Ki S Ki ; C = KSK - Ki
     {
         dim3 grid((unsigned)hm_cdiv(Mp, 8), (unsigned)Q);
         dgemv_kernel<<<grid, 256, 0, s>>>(e->Ki, e->mp, e->alpha, Mp);
         HM_CUDA(cudaGetLastError());
     }
+    HM_CUDA(cudaStreamWaitEvent(s, e->ev_S, 0));
     HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->S, Mp, sQ, e->Ki, Mp, sQ, 0.0, e->SK, Mp, sQ, Q));
     HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->Ki, Mp, sQ, e->SK, Mp, sQ, 0.0, e->KSK, Mp, sQ, Q));
     {
@@ -539,8 +557,15 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
         make_c_kernel<<<(unsigned)hm_cdiv(n, 256), 256, 0, s>>>(e->KSK, e->Ki, e->C, e->Cf, n);
         HM_CUDA(cudaGetLastError());
     }
-    kl_kernel<<<Q, 1024, 0, s>>>(e->Ki, e->S, e->Sinv, e->mp, e->alpha, e->Luu, e->Lu, e->KLq, e->flags_d + HM_MAXQ, M, Mp);
-    HM_CUDA(cudaGetLastError());
+    HM_CUDA(cudaStreamWaitEvent(s, e->ev_Sinv, 0));
+    {
+        const int nblk = 48;   // <= 64 (KLpart)
+        dim3 grid((unsigned)nblk, (unsigned)Q);
+        kl_kernel<<<grid, 256, 0, s>>>(e->Ki, e->S, e->Sinv, e->mp, e->alpha, e->Luu, e->Lu, e->KLpart, e->flags_d + HM_MAXQ, M, Mp);
+        HM_CUDA(cudaGetLastError());
+        kl_finish_kernel<<<1, Q, 0, s>>>(e->KLpart, nblk, e->KLq, M);
+        HM_CUDA(cudaGetLastError());
+    }
     if (e->prec == HMOGP_PREC_TC) HM_CHECK(hm_tc_prepare(s, e->C, e->consts, e->tcinfo, e->Cb, M, Mp, e->Mc, Q));
     return 0;
 }
@@ -789,7 +814,7 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
         if (!rc && cudaMemcpy(e->jobs_d, e->jobs_h.data(), sizeof(HmGramJob) * nj, cudaMemcpyHostToDevice) != cudaSuccess) rc = HMOGP_ERR_CUDA;
         if (!rc && cudaMemset(e->tcinfo, 0, sizeof(HmTcInfo)) != cudaSuccess) rc = HMOGP_ERR_CUDA;
     }
-    A_(KLq, HM_MAXQ); A_(jitter_d, HM_MAXQ); A_(rowstat, Q * Mp * 2); A_(dzmm, Q * Xd * Mp); A_(flags_d, 2 * HM_MAXQ);
+    A_(KLq, HM_MAXQ); A_(KLpart, HM_MAXQ * 64); A_(jitter_d, HM_MAXQ); A_(rowstat, Q * Mp * 2); A_(dzmm, Q * Xd * Mp); A_(flags_d, 2 * HM_MAXQ);
     // statistics layout
     e->off_nneg = (int)T; e->off_sdv = 2 * (int)T; e->off_sma = e->off_sdv + J; e->off_svc = e->off_sma + J * (int)Q;
     e->off_dls = e->off_svc + J * (int)Q; e->off_g1 = e->off_dls + (int)Q; e->off_dz = e->off_g1 + (int)(Q * Mp);
@@ -810,6 +835,14 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
         for (int i = 0; i < 7; ++i)
             if (cudaEventCreate(&e->ev[i]) != cudaSuccess) { hm_set_error("cudaEventCreate failed"); rc = HMOGP_ERR_CUDA; break; }
     }
+    e->s2 = nullptr; e->ev_fork = e->ev_S = e->ev_Sinv = nullptr;
+    if (!rc && (cudaStreamCreateWithFlags(&e->s2, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&e->ev_S, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&e->ev_Sinv, cudaEventDisableTiming) != cudaSuccess)) {
+        hm_set_error("side stream / event creation failed");
+        rc = HMOGP_ERR_CUDA;
+    }
     if (rc) { hmogp_destroy(e); return rc; }
     *out = e;
     return 0;
@@ -826,6 +859,10 @@ void hmogp_destroy(hmogp_engine* e) {
         if (e->tk.MW[t]) cudaFree(e->tk.MW[t]);
     }
     for (int i = 0; i < 7; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_S) cudaEventDestroy(e->ev_S);
+    if (e->ev_Sinv) cudaEventDestroy(e->ev_Sinv);
+    if (e->s2) cudaStreamDestroy(e->s2);
     delete e;
 }
 
@@ -851,6 +888,7 @@ int hmogp_set_data(hmogp_engine* e, int32_t t, const double* X, const double* Y,
         HM_CUDA(cudaMalloc(&e->tk.AC[t], n * e->tk.acs * esize(e->prec)));
         HM_CUDA(cudaMalloc(&e->tk.MW[t], n * 4 * e->Q * esize(e->prec)));
         e->cap[t] = N;
+        e->tk.cap[t] = (int64_t)n;
     }
     const cudaMemcpyKind k = mem_kind == HMOGP_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     if (N > 0) {
@@ -1060,7 +1098,7 @@ int hmogp_get_rows(hmogp_engine* e, int32_t t, double* m_fd, double* v_fd, doubl
     HM_CUDA(cudaMalloc((void**)&part, sizeof(double) * e->lik_max_blocks * (2 + HM_MAXF * (1 + 2 * HM_MAXQ) + HM_MAXQ)));
     HmTasks tk = e->tk;
     void* mwtmp = nullptr;  // do not disturb the row weights of the last evaluation
-    HM_CUDA(cudaMalloc(&mwtmp, (size_t)n * 4 * e->Q * esize(e->prec)));
+    HM_CUDA(cudaMalloc(&mwtmp, (size_t)e->tk.cap[t] * 4 * e->Q * esize(e->prec)));   // same SoA stride as AC
     tk.MW[t] = mwtmp;
     int rc = hm_lik_rows(e->stream, simt_prec, tk, e->consts, t, true, e->has_chain, part, e->lik_max_blocks, &nb, rm, rv, rve, rdm, rdv);
     if (!rc) {

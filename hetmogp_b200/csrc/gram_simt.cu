@@ -115,7 +115,7 @@ gram_kernel(HmTasks tk, HmProjArgs pa, double* Hpart, int nsplit, int64_t nblk_t
                 const double x = ok ? tk.X[t][(tk.begin[t] + row) * Xd + i] : 0.0;
                 SplitX2<T>::split(x, xh[e * Xd + i], xl[e * Xd + i]);
             }
-            om[e] = ok ? mw[row * 4 * Q + Q + q] : T(0);
+            om[e] = ok ? mw[(size_t)(Q + q) * tk.cap[t] + row] : T(0);
         }
         __syncthreads();
         for (int kb = 0; kb < nb; ++kb) {

@@ -42,7 +42,8 @@ struct HmLikRowArgs {
     const HmConsts* consts;
     double* partials;  // [gridDim.x][nstat]
     int want_grads, has_chain;
-    int acs;           // AC row stride (elements)
+    int acs;           // arrays in AC
+    int64_t cap;       // rows per array (SoA stride of AC / MW)
     int hyper;         // AC rows carry valid (b, e) (full step on the tensor-core path)
     HmTcInfo* tcinfo;  // tensor-core path: AC rows carry (a, c, b, e); emit the K_mn lengthscale statistic and max |omega|
     double *rows_m, *rows_v, *rows_ve, *rows_dm, *rows_dv;
@@ -64,9 +65,10 @@ __global__ void __launch_bounds__(HM_LIK_THREADS) lik_rows_kernel(HmLikRowArgs p
 
     for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < p.count;
          row += (int64_t)gridDim.x * blockDim.x) {
-        const T* ac = reinterpret_cast<const T*>(p.AC) + row * p.acs;
+        const T* ac = reinterpret_cast<const T*>(p.AC) + row;   // SoA: array k at k * cap
+        const size_t cap = (size_t)p.cap;
         T a[HM_MAXQ], c[HM_MAXQ];
-        for (int q = 0; q < Q; ++q) { a[q] = ac[q]; c[q] = ac[Q + q]; }
+        for (int q = 0; q < Q; ++q) { a[q] = ac[(size_t)q * cap]; c[q] = ac[(size_t)(Q + q) * cap]; }
         T m[HM_MAXF], v[HM_MAXF];
         int nneg = 0;
         for (int f = 0; f < F; ++f) {
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(HM_LIK_THREADS) lik_rows_kernel(HmLikRowArgs p
             }
         }
         if (p.want_grads) {
-            T* mw = reinterpret_cast<T*>(p.MW) + row * 4 * Q;
+            T* mw = reinterpret_cast<T*>(p.MW) + row;
             for (int q = 0; q < Q; ++q) {
                 T mu = 0, om = 0, muc = 0, omc = 0;
                 for (int f = 0; f < F; ++f) {
@@ -109,13 +111,13 @@ __global__ void __launch_bounds__(HM_LIK_THREADS) lik_rows_kernel(HmLikRowArgs p
                     muc += wc * o.dm[f];
                     omc += wc * w * o.dv[f];
                 }
-                mw[q] = mu;
-                mw[Q + q] = om;
-                mw[2 * Q + q] = muc;
-                mw[3 * Q + q] = omc;
+                mw[(size_t)q * cap] = mu;
+                mw[(size_t)(Q + q) * cap] = om;
+                mw[(size_t)(2 * Q + q) * cap] = muc;
+                mw[(size_t)(3 * Q + q) * cap] = omc;
                 if (p.tcinfo) {
                     // sum_m GK[n,m] |x_n - z_m|^2 = mu^c b + 2 omega^c e   (b, e from the forward epilogue, tc_fwd.cu)
-                    if (p.hyper) st[nbase + q] += (double)(muc * ac[2 * Q + q] + T(2) * omc * ac[3 * Q + q]);
+                    if (p.hyper) st[nbase + q] += (double)(muc * ac[(size_t)(2 * Q + q) * cap] + T(2) * omc * ac[(size_t)(3 * Q + q) * cap]);
                     wmax[0][q] = fmaxf(wmax[0][q], fabsf((float)om));
                     wmax[1][q] = fmaxf(wmax[1][q], fabsf((float)omc));
                 }
@@ -166,7 +168,7 @@ int hm_lik_rows(cudaStream_t s, int prec, const HmTasks& tk, const HmConsts* con
     p.Y = tk.Y[t]; p.AC = tk.AC[t]; p.MW = tk.MW[t];
     p.consts = consts; p.partials = partials;
     p.want_grads = want_grads ? 1 : 0; p.has_chain = has_chain ? 1 : 0;
-    p.acs = tk.acs; p.tcinfo = tcinfo; p.hyper = hyper ? 1 : 0;
+    p.acs = tk.acs; p.cap = tk.cap[t]; p.tcinfo = tcinfo; p.hyper = hyper ? 1 : 0;
     p.rows_m = rows_m; p.rows_v = rows_v; p.rows_ve = rows_ve; p.rows_dm = rows_dm; p.rows_dv = rows_dv;
     int64_t nb = hm_cdiv(p.count, HM_LIK_THREADS);
     if (nb > max_blocks) nb = max_blocks;

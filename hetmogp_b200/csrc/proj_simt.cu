@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) proj_kernel(HmTasks tk, HmProjArg
             const T* mw = reinterpret_cast<const T*>(tk.MW[t]);
             for (int e = tid; e < 4 * BM; e += kThreads) {
                 const int k = e / BM, r = e % BM;
-                rw[e] = (r < tr.nrows) ? mw[(tr.row0 + r) * 4 * Q + k * Q + q] : T(0);
+                rw[e] = (r < tr.nrows) ? mw[(size_t)(k * Q + q) * tk.cap[t] + tr.row0 + r] : T(0);
             }
         }
         for (int e = tid; e < 2 * BM; e += kThreads) racc[e] = 0.0;
@@ -251,8 +251,8 @@ __global__ void __launch_bounds__(kThreads, 1) proj_kernel(HmTasks tk, HmProjArg
             __syncthreads();
             T* ac = reinterpret_cast<T*>(tk.AC[t]);
             for (int r = tid; r < tr.nrows; r += kThreads) {
-                ac[(tr.row0 + r) * tk.acs + q] = T(racc[r]);
-                ac[(tr.row0 + r) * tk.acs + Q + q] = T(racc[BM + r]);
+                ac[(size_t)q * tk.cap[t] + tr.row0 + r] = T(racc[r]);
+                ac[(size_t)(Q + q) * tk.cap[t] + tr.row0 + r] = T(racc[BM + r]);
             }
         }
         __syncthreads();
@@ -298,24 +298,28 @@ int launch_proj(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, bool hyp
     return 0;
 }
 
-// largest row tile whose K tile fits ~128 KB of shared memory
-template <typename T> int pick_bm(int Mc) {
-    const int bm_max = sizeof(T) == 4 ? 64 : 32;
-    int bm = bm_max;
-    while (bm > 8 && (size_t)Mc * bm * sizeof(T) > 128 * 1024) bm /= 2;
-    return bm;
+// largest row tile whose whole shared-memory footprint (K tile, C_q stages, tables, fp64 accumulators) fits one SM
+template <typename T, bool BWD> int pick_bm(int Mc, int Xd) {
+    const size_t limit = 227 * 1024;
+    if constexpr (sizeof(T) == 4) {
+        if (proj_smem<T, 64>(Mc, Xd, BWD) <= limit) return 64;
+    }
+    if (proj_smem<T, 32>(Mc, Xd, BWD) <= limit) return 32;
+    if (proj_smem<T, 16>(Mc, Xd, BWD) <= limit) return 16;
+    if (proj_smem<T, 8>(Mc, Xd, BWD) <= limit) return 8;
+    return 0;
 }
 
 template <typename T, bool BWD> int dispatch_proj(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, bool hyper) {
-    const int bm = pick_bm<T>(a.Mc);
-    if ((size_t)a.Mc * bm * sizeof(T) > 128 * 1024 || a.Xdim > HM_MAXXD) {
+    const int bm = (a.Xdim <= HM_MAXXD) ? pick_bm<T, BWD>(a.Mc, a.Xdim) : 0;
+    if (bm == 0) {
         hm_set_error("projection kernel: M=%d (padded %d) or Xdim=%d exceeds the shared-memory tile budget", a.M, a.Mc, a.Xdim);
         return HMOGP_ERR_ARG;
     }
     if constexpr (sizeof(T) == 4) {
         if (bm == 64) return launch_proj<T, 64, BWD>(s, tk, a, hyper);
     }
-    if (bm >= 32) return launch_proj<T, 32, BWD>(s, tk, a, hyper);
+    if (bm == 32) return launch_proj<T, 32, BWD>(s, tk, a, hyper);
     if (bm == 16) return launch_proj<T, 16, BWD>(s, tk, a, hyper);
     return launch_proj<T, 8, BWD>(s, tk, a, hyper);
 }

@@ -51,28 +51,27 @@ __device__ __forceinline__ TileRef find_tile(const HmTasks& tk, int64_t tile) {
 }
 
 // ------------------------------------------------------------------------------------------- scales
-// One block per q:  cexp from max |C_q|, kexp from sigma_q^2.
-__global__ void tc_scale_kernel(const double* __restrict__ C, const HmConsts* __restrict__ cs, HmTcInfo* info, int M, int Mp) {
-    const int q = blockIdx.x;
+// max |C_q| over the M x M block (grid = (row blocks, Q); float bits are monotone for non-negative values), then
+// cexp from it and kexp from sigma_q^2.
+__global__ void tc_absmax_kernel(const double* __restrict__ C, unsigned* __restrict__ cmax, int M, int Mp) {
+    const int q = blockIdx.y;
     float mx = 0.f;
-    for (int64_t e = threadIdx.x; e < (int64_t)M * M; e += blockDim.x) {
-        const int i = (int)(e / M), j = (int)(e % M);
-        mx = fmaxf(mx, fabsf((float)C[((size_t)q * Mp + i) * Mp + j]));
-    }
-    __shared__ float sh[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int i = blockIdx.x * nwarp + warp; i < M; i += gridDim.x * nwarp)
+        for (int j = lane; j < M; j += 32) mx = fmaxf(mx, fabsf((float)C[((size_t)q * Mp + i) * Mp + j]));
     for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)blockDim.x / 32; ++w) mx = fmaxf(mx, sh[w]);
-        int e = 0;
-        if (mx > 0.f && isfinite(mx)) frexpf(mx, &e);          // mx < 2^e
-        info->cexp[q] = (mx > 0.f && isfinite(mx)) ? 14 - e : 0;
-        int ev = 0;
-        const float v = (float)cs->var[q];
-        if (v > 0.f && isfinite(v)) frexpf(v, &ev);
-        info->kexp[q] = (v > 0.f && isfinite(v)) ? 12 - ev : 0;
-    }
+    if (lane == 0 && mx == mx) atomicMax(&cmax[q], __float_as_uint(fminf(mx, 3.0e38f)));
+}
+__global__ void tc_scale_kernel(const unsigned* __restrict__ cmax, const HmConsts* __restrict__ cs, HmTcInfo* info) {
+    const int q = threadIdx.x;
+    const float mx = __uint_as_float(cmax[q]);
+    int e = 0;
+    if (mx > 0.f && isfinite(mx)) frexpf(mx, &e);          // mx < 2^e
+    info->cexp[q] = (mx > 0.f && isfinite(mx)) ? 14 - e : 0;
+    int ev = 0;
+    const float v = (float)cs->var[q];
+    if (v > 0.f && isfinite(v)) frexpf(v, &ev);
+    info->kexp[q] = (v > 0.f && isfinite(v)) ? 12 - ev : 0;
 }
 
 // ------------------------------------------------------------------------------------------- operand image of C_q
@@ -296,12 +295,13 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
             if (ch == 0 && r < tr.nrows) {
-                float* ac = reinterpret_cast<float*>(tk.AC[tr.t]) + (tr.row0 + r) * tk.acs;
-                ac[q] = (ah + al) + xb[r];
-                ac[Q + q] = ((chh + cl) + xb[128 + r]) * inv_pc;
+                float* ac = reinterpret_cast<float*>(tk.AC[tr.t]) + tr.row0 + r;   // SoA: array k at k * cap
+                const size_t cap = (size_t)tk.cap[tr.t];
+                ac[(size_t)q * cap] = (ah + al) + xb[r];
+                ac[(size_t)(Q + q) * cap] = ((chh + cl) + xb[128 + r]) * inv_pc;
                 if (hyper) {
-                    ac[2 * Q + q] = ((bh + bl) + xb[256 + r]) * inv_s2;
-                    ac[3 * Q + q] = ((eh + el) + xb[384 + r]) * inv_pc * inv_s2;
+                    ac[(size_t)(2 * Q + q) * cap] = ((bh + bl) + xb[256 + r]) * inv_s2;
+                    ac[(size_t)(3 * Q + q) * cap] = ((eh + el) + xb[384 + r]) * inv_pc * inv_s2;
                 }
             }
         }
@@ -389,7 +389,10 @@ int hm_tc_available() { return 1; }
 size_t hm_tc_image_elems(int Mc, int Q) { return (size_t)Q * Mc * Mc * 2; }   // fp16 elements (hi + lo)
 
 int hm_tc_prepare(cudaStream_t s, const double* C, const HmConsts* consts, HmTcInfo* info, void* Cb, int M, int Mp, int Mc, int Q) {
-    tc_scale_kernel<<<Q, 1024, 0, s>>>(C, consts, info, M, Mp);
+    HM_CUDA(cudaMemsetAsync(&info->cmax[0], 0, sizeof(unsigned) * HM_MAXQ, s));
+    tc_absmax_kernel<<<dim3(48, (unsigned)Q), 256, 0, s>>>(C, &info->cmax[0], M, Mp);
+    HM_CUDA(cudaGetLastError());
+    tc_scale_kernel<<<1, Q, 0, s>>>(&info->cmax[0], consts, info);
     HM_CUDA(cudaGetLastError());
     dim3 grid((unsigned)hm_cdiv(kNB * 8, 256), (unsigned)((Mc / kNB) * (Mc / kKB)), (unsigned)Q);
     tc_image_kernel<<<grid, 256, 0, s>>>(C, info, reinterpret_cast<uint16_t*>(Cb), Mp, Mc);

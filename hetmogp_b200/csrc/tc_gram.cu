@@ -21,10 +21,12 @@
 //   level 3  fp64 partial tile of this CTA in HBM/L2, every `f2` level-1 windows (16 K rows); summed in a fixed order
 //            by tc_gram_reduce_kernel -> deterministic.
 //
-// Warp roles (480 threads, 1 CTA/SM, persistent over a host-built plan of (q, tile, row-range) segments):
-//   warps 0-7   B generators (thread = column j of the tile)     warps 8-11  A generators (thread = column i)
-//   warp 12     MMA issuer (one thread)                          warps 13-14 row loaders (x, weights -> smem ring)
-//   generators also run the level-2/3 flushes (12 warps: 4 lane quadrants x 3 column groups).
+// Warp roles (608 threads, 1 CTA/SM, persistent over a host-built plan of (q, tile, row-range) segments):
+//   warps 0-7   B generators (thread = column j of the tile, all 32 rows of the chunk)
+//   warps 8-15  A generators (thread = column i; the A operand costs ~1.5x per element -- weights, g-vectors -- and gates
+//               every stage, so each A column group is split over two warps, 16 rows each)
+//   warp 16     MMA issuer (one thread)                          warps 17-18 row loaders (x, weights -> smem ring)
+//   Generators also run the level-2/3 flushes (4 TMEM lane quadrants x 4 column groups).
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -38,8 +40,10 @@ constexpr int kGAHalf = 128 * 64;                        //  8 KB : A hi (or lo)
 constexpr int kGStageBytes = 2 * kGBHalf + 2 * kGAHalf;  // 48 KB
 constexpr int kRowSlots = 8;
 constexpr int kRowArrays = 16;   // arrays per slot, each [kGC] floats (SoA): xh[XD] | xl[XD] | w | v0..v4
-constexpr int kGThreads = 480;
-constexpr int kGenWarps = 12;
+constexpr int kSplitA = HM_GRAM_ROWSPLIT;      // A-generator warps per column group: each takes kGC / kSplitA rows of a chunk
+constexpr int kGenWarps = 8 + 4 * kSplitA;     // 8 B column groups (all rows) + 4 A column groups x row parts
+constexpr int kMmaWarp = kGenWarps;            // + 2 row-loader warps
+constexpr int kGThreads = (kGenWarps + 3) * 32;
 constexpr uint32_t kAcc2 = 256;  // TMEM column of the level-2 accumulator
 
 struct GramBars {
@@ -99,7 +103,7 @@ tc_gram_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, con
         mbar_init(&sb->accempty, kGenWarps);
         mbar_fence_init();
     }
-    if (warp == 12) tmem_alloc(&sb->tmem_base, 512u);
+    if (warp == kMmaWarp) tmem_alloc(&sb->tmem_base, 512u);
     fence_before();
     __syncthreads();
     fence_after();
@@ -107,8 +111,10 @@ tc_gram_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, con
 
     if (warp < kGenWarps) {
         // ======================================================= generators (+ level-2/3 flushes)
-        const bool isA = warp >= 8;
-        const int col = isA ? (int)threadIdx.x - 256 : (int)threadIdx.x;   // row of the operand tile this thread writes
+        const bool isA = warp >= 8;                                        // warps 0-7: B column groups; 8..: A (column group, row part)
+        const int cg = isA ? 8 + (warp - 8) % 4 : warp, rh = isA ? (warp - 8) / 4 : 0;
+        const int col = (isA ? cg - 8 : cg) * 32 + lane;                   // row of the operand tile this thread writes
+        constexpr int kN8A = kGC / 8 / kSplitA;                            // groups of 8 rows per A thread and chunk
         const int swz = (col >> 1) & 3;                                    // SW64: chunk ^= (row >> 1) & 3
         const int wdim = gw.wdim[0];
         uint32_t cc_ = 0;     // chunk counter (stage / row-slot rings)
@@ -124,29 +130,29 @@ tc_gram_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, con
             const int lq = warp & 3, wq = warp >> 2;
             const int i = lq * 32 + lane;
             const uint32_t tl = tmem_base + ((uint32_t)(lq * 32) << 16);
-            for (int cc = wq; cc < pd.ncc; cc += 3) {
-                uint32_t v[32];
-                tmem_ld32(tl + cc * 32, v);
+            for (int c16 = wq; c16 < 2 * pd.ncc; c16 += kGenWarps / 4) {   // units of 16 columns
+                uint32_t v[16];
+                tmem_ld16(tl + c16 * 16, v);
                 if (!pd.acc2_fresh) {
-                    uint32_t u[32];
-                    tmem_ld32(tl + kAcc2 + cc * 32, u);
+                    uint32_t u[16];
+                    tmem_ld16(tl + kAcc2 + c16 * 16, u);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int p = 0; p < 32; ++p) v[p] = __float_as_uint(__uint_as_float(v[p]) + __uint_as_float(u[p]));
+                    for (int p = 0; p < 16; ++p) v[p] = __float_as_uint(__uint_as_float(v[p]) + __uint_as_float(u[p]));
                 } else {
                     tmem_ld_wait();
                 }
                 if (!pd.to_l3) {
-                    tmem_st32(tl + kAcc2 + cc * 32, v);
+                    tmem_st16(tl + kAcc2 + c16 * 16, v);
                 } else {
-                    double2* dst = reinterpret_cast<double2*>(pd.slot + ((size_t)i * 256 + cc * 32));
+                    double2* dst = reinterpret_cast<double2*>(pd.slot + ((size_t)i * 256 + c16 * 16));
                     if (pd.slot_fresh) {
 #pragma unroll
-                        for (int p = 0; p < 16; ++p)
+                        for (int p = 0; p < 8; ++p)
                             dst[p] = make_double2((double)__uint_as_float(v[2 * p]) * pd.inv_sc, (double)__uint_as_float(v[2 * p + 1]) * pd.inv_sc);
                     } else {
 #pragma unroll
-                        for (int p = 0; p < 16; ++p) {
+                        for (int p = 0; p < 8; ++p) {
                             double2 o = dst[p];
                             o.x += (double)__uint_as_float(v[2 * p]) * pd.inv_sc;
                             o.y += (double)__uint_as_float(v[2 * p + 1]) * pd.inv_sc;
@@ -281,14 +287,18 @@ tc_gram_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, con
                             }
                         };
                         RowX<XD> r0, r1;
-                        load_rowx<XD>(r0, rb, 0);
-                        load_rowx<XD>(r1, rb, 1);
-                        gen_a(r0, 0);
-                        load_rowx<XD>(r0, rb, 2);
-                        gen_a(r1, 1);
-                        load_rowx<XD>(r1, rb, 3);
-                        gen_a(r0, 2);
-                        gen_a(r1, 3);
+                        static_assert(kN8A == 2 || kN8A == 4, "A generator pipeline: 2 or 4 groups of 8 rows per thread");
+                        const int nb = rh * kN8A;
+                        load_rowx<XD>(r0, rb, nb);
+                        load_rowx<XD>(r1, rb, nb + 1);
+                        gen_a(r0, nb);
+                        if (kN8A == 4) load_rowx<XD>(r0, rb, nb + 2);
+                        gen_a(r1, nb + 1);
+                        if (kN8A == 4) {
+                            load_rowx<XD>(r1, rb, nb + 3);
+                            gen_a(r0, nb + 2);
+                            gen_a(r1, nb + 3);
+                        }
                         if (NV > 0 && sg.has_g) {
 #pragma unroll
                             for (int v = 0; v < NV; ++v) g64[v] += (double)(g2[v].x + g2[v].y);
@@ -311,14 +321,14 @@ tc_gram_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, con
                 if (pend.to_l3) { slot_fresh = false; acc2_fresh = true; } else acc2_fresh = false;
                 ++iv;
             }
-            if (NV > 0 && isA && sg.has_g) {
-                double* gdst = slot + (size_t)128 * 256;
+            if (NV > 0 && isA && sg.has_g) {   // one partial per row part; tc_gram_reduce_kernel adds them
+                double* gdst = slot + (size_t)128 * 256 + (size_t)rh * HM_GRAM_MAXV * 128;
 #pragma unroll
                 for (int v = 0; v < NV; ++v) gdst[v * 128 + col] = g64[v];
             }
         }
         if (pend.on) flush_window(pend);
-    } else if (warp == 12) {
+    } else if (warp == kMmaWarp) {
         // ======================================================= MMA issuer (one thread)
         if (lane == 0) {
             uint32_t cc_ = 0, iv = 0;
@@ -354,7 +364,7 @@ tc_gram_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, con
         // ======================================================= row loaders (2 warps, alternating groups of 4 chunks)
         // Each iteration issues the global loads of 4 chunks (128 rows) before touching the ring: memory-level
         // parallelism instead of one exposed HBM/L2 latency per chunk.
-        const int rw = warp - 13;
+        const int rw = warp - (kMmaWarp + 1);
         constexpr int kGrp = 4;
         int nch[HM_MAXT];
         for (int t = 0; t < HM_MAXT; ++t) nch[t] = (t < tk.T) ? (int)((tk.count[t] + kGC - 1) / kGC) : 0;
@@ -380,10 +390,11 @@ tc_gram_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, con
                         if (mine) {
 #pragma unroll
                             for (int i = 0; i < XD; ++i) xv[j][i] = valid ? tk.X[t][(tk.begin[t] + row) * XD + i] : 0.0;
-                            const float* mw = reinterpret_cast<const float*>(tk.MW[t]) + row * 4 * Q;
-                            wv[j] = valid ? mw[gw.wbase[0] * Q + q] : 0.f;
+                            const float* mw = reinterpret_cast<const float*>(tk.MW[t]) + row;   // SoA: array k at k * cap
+                            const size_t cap = (size_t)tk.cap[t < tk.T ? t : 0];
+                            wv[j] = valid ? mw[(size_t)(gw.wbase[0] * Q + q) * cap] : 0.f;
 #pragma unroll
-                            for (int v = 0; v < NV; ++v) vv[j][v] = valid ? mw[gw.vbase[v] * Q + q] : 0.f;
+                            for (int v = 0; v < NV; ++v) vv[j][v] = valid ? mw[(size_t)(gw.vbase[v] * Q + q) * cap] : 0.f;
                         }
                         if (++ct >= nch[t]) { ct = 0; ++t; while (t < tk.T && nch[t] == 0) ++t; }
                     }
@@ -416,7 +427,7 @@ tc_gram_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, con
     // ---- teardown
     fence_before();
     __syncthreads();
-    if (warp == 12) tmem_dealloc(tmem_base, 512u);
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512u);
 }
 
 // Sum the partial tiles of every (q, tile job) in slot order; write H (lower from the tile; mirrored if symmetric) and g^v.
@@ -440,7 +451,9 @@ __global__ void tc_gram_reduce_kernel(const double* __restrict__ slots, const Hm
             const int v = e / 128, i = e % 128;
             if (jb.I * 128 + i >= M) continue;
             double s = 0.0;
-            for (int sl = sr.x; sl < sr.y; ++sl) s += slots[(size_t)sl * HM_GRAM_SLOT_DOUBLES + (size_t)128 * 256 + v * 128 + i];
+            for (int sl = sr.x; sl < sr.y; ++sl)
+                for (int rh = 0; rh < HM_GRAM_ROWSPLIT; ++rh)
+                    s += slots[(size_t)sl * HM_GRAM_SLOT_DOUBLES + (size_t)128 * 256 + (size_t)(rh * HM_GRAM_MAXV + v) * 128 + i];
             g0[(size_t)v * gstride + (size_t)q * Mp + jb.I * 128 + i] = s;
         }
     }

@@ -222,33 +222,37 @@ def test_shard_sum_equals_whole_large_n():
     import torch
     from hetmogp_b200 import _lib, shard_rows
     prob = synth.make_problem([("Gaussian", 0.5), ("Bernoulli",), ("Poisson",)], 60000, 200, 3, seed=21)
-    eng = pu.make_engine(prob, "fp32")
-    p = pu.params_of(prob)
-    whole = eng.evaluate(p, what="full")
-    n = int(_lib.lib.hmogp_stats_len(eng._h))
-    acc = torch.zeros(n, dtype=torch.float64, device="cuda")
-    buf = torch.empty(n, dtype=torch.float64, device="cuda")
-    keep = []
-    ps = eng._params(p, keep)
-    N = [x.shape[0] for x in prob["X"]]
-    for r in range(4):
-        eng.set_rows(*shard_rows(N, r, 4))
-        _lib.check(_lib.lib.hmogp_step_local(eng._h, C.byref(ps), 0, 2, C.c_void_p(buf.data_ptr())))
-        torch.cuda.synchronize()
-        acc += buf
-    out, gs = eng._alloc_out(2, False, True)
-    st = _lib.Status()
-    _lib.check(_lib.lib.hmogp_step_finish(eng._h, C.c_void_p(acc.data_ptr()), C.byref(gs), 0, 2, C.byref(st)))
-    assert abs(out["log_marginal"][0, 0] - whole["log_marginal"][0, 0]) < 1e-9 * abs(whole["log_marginal"][0, 0])
-    for k in GRADS:
-        assert pu.relerr(out[k], whole[k]) < 2e-5, k
+    # fp64 mode: the identity is exact up to fp64 round-off.  (In the fp32-class modes the Gram tiles of a shard and of
+    # the whole are rounded at different row boundaries; K_uu^-1 H K_uu^-1 amplifies that 1e-7 to ~4e-3 on dL_dL_u --
+    # checked below with the tolerance that sensitivity implies.)
+    for prec, tol_elbo, tol_grad in (("fp64", 1e-12, 1e-9), ("tc", 1e-7, 2e-2)):
+        eng = pu.make_engine(prob, prec)
+        p = pu.params_of(prob)
+        whole = eng.evaluate(p, what="full")
+        n = int(_lib.lib.hmogp_stats_len(eng._h))
+        acc = torch.zeros(n, dtype=torch.float64, device="cuda")
+        buf = torch.empty(n, dtype=torch.float64, device="cuda")
+        keep = []
+        ps = eng._params(p, keep)
+        N = [x.shape[0] for x in prob["X"]]
+        for r in range(4):
+            eng.set_rows(*shard_rows(N, r, 4))
+            _lib.check(_lib.lib.hmogp_step_local(eng._h, C.byref(ps), 0, 2, C.c_void_p(buf.data_ptr())))
+            torch.cuda.synchronize()
+            acc += buf
+        out, gs = eng._alloc_out(2, False, True)
+        st = _lib.Status()
+        _lib.check(_lib.lib.hmogp_step_finish(eng._h, C.c_void_p(acc.data_ptr()), C.byref(gs), 0, 2, C.byref(st)))
+        assert abs(out["log_marginal"][0, 0] - whole["log_marginal"][0, 0]) < tol_elbo * abs(whole["log_marginal"][0, 0])
+        for k in GRADS:
+            assert pu.relerr(out[k], whole[k]) < tol_grad, (prec, k, pu.relerr(out[k], whole[k]))
+        eng.close()
     # and against the oracle on a bounded row sample (oracle cost is linear in N)
     sub = synth.subsample(prob, 4000)
     eng2 = pu.make_engine(sub, "fp32")
     o = diag_oracle.elbo_and_grads(sub)
     e2 = eng2.evaluate(pu.params_of(sub), what="full")
     assert abs(e2["log_marginal"][0, 0] - o["log_marginal"][0, 0]) < 1e-4 * abs(o["log_marginal"][0, 0])
-    eng.close()
     eng2.close()
 
 

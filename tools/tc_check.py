@@ -44,8 +44,15 @@ def timed(eng, p, what, reps=3):
     return out, best
 
 
+def make_cfg(cfg, N):
+    """cfg1..cfg4 of BASELINE.json, or 'sweepM<M>' = cfg5's inducing-point sweep (cfg2's likelihood list)."""
+    if cfg.startswith("sweepM"):
+        return synth.make_problem([("Gaussian", 0.5), ("Bernoulli",), ("Poisson",)], N, int(cfg[6:]), 3, 1, seed=1239)
+    return synth.make_config(cfg, N=N)
+
+
 def scale(cfg, N, ref_prec="fp64", whats=("full",)):
-    prob = synth.make_config(cfg, N=N)
+    prob = make_cfg(cfg, N)
     p = pu.params_of(prob)
     eng = pu.make_engine(prob, "tc")
     outs = {}
@@ -65,6 +72,7 @@ def scale(cfg, N, ref_prec="fp64", whats=("full",)):
     print("PARITY %s N=%d tc vs %s: elbo=%.12g ref=%.12g rel=%.2e  " % (cfg, N, ref_prec, out["log_marginal"][0, 0],
                                                                       o["log_marginal"][0, 0], e) +
           "  ".join("%s=%.2e" % (k, pu.relerr(out[k], o[k])) for k in GRADS))
+    print("D_RBF tc ", np.array2string(out["d_rbf"].ravel(), precision=6), " ref", np.array2string(o["d_rbf"].ravel(), precision=6))
     if os.environ.get("TC_CHECK_FP32"):
         e32 = pu.make_engine(prob, "fp32")
         o32, tm = timed(e32, p, "full", reps=1)
