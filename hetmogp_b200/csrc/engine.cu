@@ -108,7 +108,7 @@ __global__ void kl_kernel(const double* Ki, const double* S, const double* Sinv,
         const int64_t ro = base + (int64_t)i * Mp;
         for (int j = lane; j < M; j += 32) {
             s += 0.5 * Ki[ro + j] * S[ro + j];
-            if (isinf(Sinv[ro + j])) bad = 1;
+            if (!isfinite(Sinv[ro + j])) bad = 1;   // inf (svmogp_inf.py:126) or the NaN an inf turns into downstream
         }
         if (lane == 0) {
             s += 0.5 * mp[(int64_t)q * Mp + i] * alpha[(int64_t)q * Mp + i];
