@@ -164,31 +164,38 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
     const uint32_t tmem_base = sb->tmem_base;
 
     if (warp < kGenWarps) {
-        // ======================================================= generators: thread = row, warp = (row quadrant, column half)
-        const int r = (warp & 3) * 32 + lane, ch = warp >> 2;
+        // ======================================================= generators: thread = 2 rows (lane, lane + 32 of a 64-row
+        // half), warp = (row half, column quarter): the per-column table values are loaded once for both rows
+        const int rg = warp & 1, cq = warp >> 1;
+        const int r0 = rg * 64 + lane, r1 = r0 + 32;
         int stage = 0; uint32_t phase = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const TileRef tr = find_tile(tk, tile);
-            float xh[XD], xl[XD];
+            float2 xh0[XD], xl0[XD], xh1[XD], xl1[XD];
 #pragma unroll
             for (int i = 0; i < XD; ++i) {
-                const double x = (r < tr.nrows) ? tk.X[tr.t][(tk.begin[tr.t] + tr.row0 + r) * XD + i] : 0.0;
-                split_scaled(x, sscale, xh[i], xl[i]);
+                const double xa = (r0 < tr.nrows) ? tk.X[tr.t][(tk.begin[tr.t] + tr.row0 + r0) * XD + i] : 0.0;
+                const double xb_ = (r1 < tr.nrows) ? tk.X[tr.t][(tk.begin[tr.t] + tr.row0 + r1) * XD + i] : 0.0;
+                float h, l;
+                split_scaled(xa, sscale, h, l); xh0[i] = dup2(h); xl0[i] = dup2(l);
+                split_scaled(xb_, sscale, h, l); xh1[i] = dup2(h); xl1[i] = dup2(l);
             }
             for (int h = 0; h < nhalf; ++h) {
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait_warp(&sb->empty[stage], phase ^ 1);
-                    uint8_t* a_hi = stage_base + (size_t)stage * kStageBytes + r * 128;
-                    uint8_t* a_lo = a_hi + kAHalf;
+                    uint8_t* a0_hi = stage_base + (size_t)stage * kStageBytes + r0 * 128;
+                    uint8_t* a1_hi = stage_base + (size_t)stage * kStageBytes + r1 * 128;
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        const int c = ch * 4 + cc;
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int c = cq * 2 + cc;
                         const float4* t4 = reinterpret_cast<const float4*>(tab + (size_t)(kb * 8 + c) * R * 8);
-                        float2 e[4];   // d.d - bias for the 8 columns, as 4 pairs
+                        float2 e0[4], e1[4];   // d.d - bias for the 8 columns (4 pairs), rows r0 / r1
                         {
                             const float4 b0 = t4[(2 * XD) * 2], b1 = t4[(2 * XD) * 2 + 1];
-                            e[0] = make_float2(b0.x, b0.y); e[1] = make_float2(b0.z, b0.w);
-                            e[2] = make_float2(b1.x, b1.y); e[3] = make_float2(b1.z, b1.w);
+                            e0[0] = make_float2(b0.x, b0.y); e0[1] = make_float2(b0.z, b0.w);
+                            e0[2] = make_float2(b1.x, b1.y); e0[3] = make_float2(b1.z, b1.w);
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) e1[p] = e0[p];
                         }
 #pragma unroll
                         for (int i = 0; i < XD; ++i) {
@@ -196,19 +203,25 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
                             const float4 l0 = t4[(2 * i + 1) * 2], l1 = t4[(2 * i + 1) * 2 + 1];
                             const float2 nzh[4] = {make_float2(h0.x, h0.y), make_float2(h0.z, h0.w), make_float2(h1.x, h1.y), make_float2(h1.z, h1.w)};
                             const float2 nzl[4] = {make_float2(l0.x, l0.y), make_float2(l0.z, l0.w), make_float2(l1.x, l1.y), make_float2(l1.z, l1.w)};
-                            const float2 xh2 = dup2(xh[i]), xl2 = dup2(xl[i]);
 #pragma unroll
                             for (int p = 0; p < 4; ++p) {
-                                const float2 d = add2(add2(xh2, nzh[p]), add2(xl2, nzl[p]));
-                                e[p] = fma2(d, d, e[p]);
+                                const float2 da = add2(add2(xh0[i], nzh[p]), add2(xl0[i], nzl[p]));
+                                const float2 db = add2(add2(xh1[i], nzh[p]), add2(xl1[i], nzl[p]));
+                                e0[p] = fma2(da, da, e0[p]);
+                                e1[p] = fma2(db, db, e1[p]);
                             }
                         }
                         uint32_t hi[4], lo[4];
 #pragma unroll
-                        for (int p = 0; p < 4; ++p) split2(ex2(-e[p].x), ex2(-e[p].y), hi[p], lo[p]);
-                        const int off = (c ^ (r & 7)) << 4;
-                        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        for (int p = 0; p < 4; ++p) split2(ex2(-e0[p].x), ex2(-e0[p].y), hi[p], lo[p]);
+                        int off = (c ^ (r0 & 7)) << 4;
+                        *reinterpret_cast<uint4*>(a0_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(a0_hi + kAHalf + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) split2(ex2(-e1[p].x), ex2(-e1[p].y), hi[p], lo[p]);
+                        off = (c ^ (r1 & 7)) << 4;
+                        *reinterpret_cast<uint4*>(a1_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(a1_hi + kAHalf + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                     fence_async_smem();            // generic-proxy stores -> visible to the tensor-core (async) proxy
                     __syncwarp();
