@@ -86,14 +86,14 @@ class ClockSampler(threading.Thread):
 
 
 def algorithmic_work(N_tasks, M, Q, Xdim, what="full"):
-    """U = (sum_t Q N_t) M^2 multiply-adds.  Forward quadratic form 2U flops; every weighted Gram of
-    the backward pass is symmetric-aware U flops: one (H^1) in a VE step, 1 + Xdim (H^1 and the distance-weighted
-    D^i) in a full step  =>  full step (3 + Xdim) U on the Gram formulation (the SIMT path recomputes the projection
-    instead: (4 + Xdim) U).  Irreducible HBM bytes: sum_t N_t (Xdim + 1) 8."""
+    """U = (sum_t Q N_t) M^2 multiply-adds.  Forward quadratic form 2U flops; the weighted Gram H^1 of
+    the backward pass is symmetric-aware U flops; the hyper-parameter column statistics of a full step need the
+    projection again (transposed): 2U  =>  ELBO only 2U, VE step 3U, full step 5U.  Irreducible HBM bytes:
+    sum_t N_t (Xdim + 1) 8."""
     P = sum(Q * n for n in N_tasks)
     U = float(P) * M * M
-    n_gram = {"elbo": 0, "ve": 1, "full": 1 + Xdim}[what]
-    return dict(U=U, flops_full=(2 + n_gram) * U, flops_fwd=2 * U, flops_bwd_proj=2 * U, flops_gram=U, n_gram=n_gram,
+    fl = {"elbo": 2.0, "ve": 3.0, "full": 5.0}[what]
+    return dict(U=U, flops_full=fl * U, flops_fwd=2 * U, flops_bwd_proj=2 * U, flops_gram=U,
                 bytes=float(sum(N_tasks)) * (Xdim + 1) * 8)
 
 
@@ -268,9 +268,10 @@ def main():
     med = {k: float(np.median([p[k] for p in phases])) for k in phases[0] if k.endswith("_ms")}
     # (kernel name, algorithmic flops per launch, launches per step) of the N-sized kernels behind each phase timer
     if prec == "tc":
-        kern = {"forward_ms": ("tc_fwd_kernel (K_fu build + K_fu C_q on tcgen05 + row reductions)", work["flops_fwd"], 1),
-                "bwd_gram_ms": ("tc_gram_kernel (K_fu^T diag(w) K_fu on tcgen05, one launch per weight)", work["flops_gram"],
-                                max(1, work["n_gram"]))}
+        kern = {"forward_ms": ("tc_fwd_kernel (K_fu build + K_fu C_q on tcgen05 cta_group::2 + row reductions)", work["flops_fwd"], 1),
+                "bwd_gram_ms": ("tc_gram_kernel (H^1 = K_fu^T diag(omega) K_fu on tcgen05, three-level accumulation)", work["flops_gram"], 1)}
+        if args.what == "full":
+            kern["bwd_proj_ms"] = ("tc_bwd_kernel (transposed projection C_q K_fu^T on tcgen05 cta_group::2 + column sums)", work["flops_bwd_proj"], 1)
     else:
         kern = {"forward_ms": ("proj_fwd (K_fu build + projection)", work["flops_fwd"], 1),
                 "bwd_proj_ms": ("proj_bwd (K_fu rebuild + projection + hyper column stats)", work["flops_bwd_proj"], 1),
@@ -281,18 +282,18 @@ def main():
     n_kernel_ms = sum(med.get(k, 0.0) for k in kern)
     Mc = -(-M // 256) * 256
     issued = {"forward_ms": 3 * 2.0 * work["U"] / (M * M) * Mc * Mc,                       # 3 split-fp16 products, padded M
+              "bwd_proj_ms": 3 * 2.0 * work["U"] / (M * M) * Mc * Mc,
               "bwd_gram_ms": 3 * 2.0 * work["U"] / (M * M) * (Mc * Mc) * 0.625}            # lower block-triangle of 128x256 tiles
-    traffic = {"tc_gram_kernel": 1.03e9, "tc_fwd_kernel": 3.1e8}   # dram read+write per launch, ncu --set full (profiles/r1_tc_ncu_summary.txt)
+    traffic = {"bwd_gram_ms": 1.03e9, "forward_ms": 3.1e8, "bwd_proj_ms": None}   # dram read+write per launch, ncu --set full (profiles/r1_tc_ncu_summary.txt)
     roofline = {"bound": "tensor", "kernel": kern[dom][0], "achieved": ach, "peak": peaks["tc"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tc"],
-                "traffic": (traffic["tc_gram_kernel"] if dom == "bwd_gram_ms" else traffic["tc_fwd_kernel"]) if (prec == "tc" and args.config == "cfg3" and world == 1 and not args.rows) else None,
+                "traffic": traffic.get(dom) if (prec == "tc" and args.config == "cfg3" and world == 1 and not args.rows) else None,
                 "peak_source": peaks["src"] + " bf16 sustained (kernel timed inside a long step)",
                 "operand_format": {"tc": "split-fp16 hi/lo, 3 tcgen05.mma products per algorithmic product (fp32-class accuracy); "
                                          "the algorithmic fraction is therefore bounded by 1/3 of the bf16 peak",
                                    "fp32": "fp32 FFMA (CUDA cores)", "fp64": "fp64 DFMA"}[prec],
                 "algorithmic_flops_per_launch": kern[dom][1], "ms_per_launch": per_launch[dom], "launches_per_step": kern[dom][2],
-                "issued_mma_tflops": ({k: issued[k] * (kern[k][2] if k == "bwd_gram_ms" else 1) / (med[k] * 1e-3) / 1e12
-                                       for k in kern if med.get(k, 0) > 0} if prec == "tc" else None),
+                "issued_mma_tflops": ({k: issued[k] / (med[k] * 1e-3) / 1e12 for k in kern if med.get(k, 0) > 0} if prec == "tc" else None),
                 "all_kernels": {kern[k][0].split(" ")[0]: {"ms_per_launch": per_launch[k], "launches": kern[k][2],
                                                             "achieved_TFLOPs": kern[k][1] / (per_launch[k] * 1e-3) / 1e12 if per_launch[k] > 0 else 0.0}
                                 for k in kern},

@@ -132,7 +132,9 @@ int hm_tc_available();
 size_t hm_tc_image_elems(int Mc, int Q);
 int hm_tc_prepare(cudaStream_t s, const double* C, const HmConsts* consts, HmTcInfo* info, void* Cb, int M, int Mp, int Mc, int Q);
 int hm_tc_proj_fwd(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const void* Cb, const HmTcInfo* info, bool hyper,
-                   int npass);
+                   int npass, int ncta);
+int hm_tc_proj_bwd(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const void* Cb, const HmTcInfo* info, double* colpart,
+                   int nslots, int npass);
 int hm_tc_gram(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const HmTcInfo* info, const HmGramSeg* segs,
                const int* seg_off, const HmGramWeights& gw, double* slots, int nctas, int f1, int f2, int npass);
 int hm_tc_gram_reduce(cudaStream_t s, const double* slots, const HmGramJob* jobs, const int2* jobslots, int njobs, int Q,

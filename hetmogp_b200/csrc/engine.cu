@@ -159,7 +159,7 @@ __global__ void reduce_col_kernel(const double* colpart, int nworkers, int ncol,
     if (i >= ncol) return;
     double s = 0.0;
     for (int w = 0; w < nworkers; ++w) s += colpart[((int64_t)q * nworkers + w) * ncol + i];
-    if (i == ncol - 1) dls[q] = s;
+    if (i == ncol - 1) { if (dls) dls[q] = s; }
     else {
         const int k = i / Mc, m = i % Mc;
         if (k == 0) g1[(int64_t)q * Mp + m] = s;
@@ -342,38 +342,6 @@ __global__ void extract_mm_kernel(const double* src, double* dst, int M, int Mp,
     dst[((int64_t)q * M + i) * M + j] = (lower_only && j > i) ? 0.0 : src[((int64_t)q * Mp + i) * Mp + j];
 }
 
-// Inducing-input statistic of the K_mn chain from the distance-weighted Grams (tensor-core path):
-//   dz[q][i][m] = sum_n GK[n,m] (x_ni - z_mi) = (1/s) [ alpha_m g^{d_i}_m + 2 sum_j C[m,j] D^i[m,j] ]
-// with D^i[m,j] = sum_n omega^c s (x_ni - z_mi) K[n,m] K[n,j] stored for j <= m and, for j > m,
-//   D^i[m,j] = D^i[j,m] + s (z_ji - z_mi) H^1[j,m]
-// (reference: RBF.gradients_X(dL_dKmn, Z, X), svmogp.py:153-156).  One warp per (q, m).
-__global__ void gram_dz_kernel(const double* __restrict__ C, const double* __restrict__ alpha, const double* __restrict__ Zp,
-                               const HmConsts* __restrict__ cs, const double* __restrict__ H1, const double* __restrict__ Dx,
-                               int64_t hstride, const double* __restrict__ gd, int64_t gstride, double* dz, int M, int Mp,
-                               int Xd) {
-    const int q = blockIdx.y;
-    const int m = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
-    if (m >= M) return;
-    const double sscale = sqrt(0.5 * 1.4426950408889634 * cs->inv_l2[q]);
-    const size_t qoff = (size_t)q * Mp * Mp, rowoff = qoff + (size_t)m * Mp;
-    for (int i = 0; i < Xd; ++i) {
-        const double zm = Zp[((size_t)q * Mp + m) * Xd + i];
-        const double* D = Dx + (size_t)i * hstride;
-        double s = 0.0;
-        for (int j = lane; j < M; j += 32) {
-            double dmj;
-            if (j <= m) dmj = D[rowoff + j];
-            else dmj = D[qoff + (size_t)j * Mp + m] + sscale * (Zp[((size_t)q * Mp + j) * Xd + i] - zm) * H1[qoff + (size_t)j * Mp + m];
-            s += C[rowoff + j] * dmj;
-        }
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (lane == 0) {
-            const size_t vi = (size_t)q * Mp + m;
-            dz[((size_t)q * Xd + i) * Mp + m] = (alpha[vi] * gd[(size_t)i * gstride + vi] + 2.0 * s) / sscale;
-        }
-    }
-}
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ engine state
@@ -397,12 +365,12 @@ struct hmogp_engine {
     void* Cb;              // split-fp16 SW128 operand image of C
     HmTcInfo* tcinfo;
     int tc_npass, tc_f1, tc_f2;   // MMA passes; level-1 window (chunks); level-3 period (windows)
+    int tc_ncta;                  // forward kernel: 1 = one CTA per SM, 2 = cta_group::2 CTA pairs
     std::vector<HmGramJob> jobs_h;
     HmGramJob* jobs_d;
     HmGramSeg* segs_d; int* segoff_d; int2* jobslots_d;
     int max_segs, nslots_max;
     double* slots;         // [nslots][HM_GRAM_SLOT_DOUBLES] fp64 partial tiles
-    double* Hx;            // [1 + Xd][Q][Mp][Mp] extra Grams
     double* gvec;          // [HM_GRAM_MAXV][Q][Mp]
     bool plan_dirty;
     double *KLq, *KLpart, *jitter_d, *rowstat, *dzmm;
@@ -648,38 +616,26 @@ int tc_backward(hmogp_engine* e, int what, double* stats) {
     const int64_t MM = (int64_t)Q * Mp * Mp, gstride = (int64_t)Q * Mp;
     HM_CHECK(build_gram_plan(e));
     HmProjArgs pa = proj_args(e);
-    const bool full = what >= HMOGP_WHAT_FULL, chain = e->has_chain;
-    // weight list: index 0 -> H (E statistic); the rest -> Hx scratch in order
-    int wb[2 + HM_MAXXD], wd[2 + HM_MAXXD], nWt = 0;
-    wb[nWt] = 1; wd[nWt++] = -1;
+    const bool full = what >= HMOGP_WHAT_FULL;
     if (full) {
-        if (chain) { wb[nWt] = 3; wd[nWt++] = -1; }
-        for (int i = 0; i < Xd; ++i) { wb[nWt] = chain ? 3 : 1; wd[nWt++] = i; }
-    }
-    HM_CUDA(cudaMemsetAsync(stats + e->off_H, 0, sizeof(double) * MM, s));
-    if (nWt > 1) HM_CUDA(cudaMemsetAsync(e->Hx, 0, sizeof(double) * MM * (nWt - 1), s));
-    for (int w0 = 0; w0 < nWt; ++w0) {
-        HmGramWeights gw;
-        memset(&gw, 0, sizeof(gw));
-        gw.nW = 1; gw.wbase[0] = wb[w0]; gw.wdim[0] = wd[w0]; gw.wdim[1] = -1;
-        if (w0 == 0) {
-            gw.vbase[gw.nV] = 0; gw.vdim[gw.nV++] = -1;                       // g^mu -> dVE/dm
-            if (full)
-                for (int i = 0; i < Xd; ++i) { gw.vbase[gw.nV] = chain ? 2 : 0; gw.vdim[gw.nV++] = i; }   // sum_n mu^c s d_i K
-        }
-        HM_CHECK(hm_tc_gram(s, e->tk, pa, e->tcinfo, e->segs_d, e->segoff_d, gw, e->slots, e->nworkers, e->tc_f1, e->tc_f2, e->tc_npass));
-        double* H = (w0 == 0) ? stats + e->off_H : e->Hx + (int64_t)(w0 - 1) * MM;
-        HM_CHECK(hm_tc_gram_reduce(s, e->slots, e->jobs_d, e->jobslots_d, (int)e->jobs_h.size(), Q, gw, H, e->gvec, gstride, M, Mp));
-    }
-    HM_CUDA(cudaMemcpyAsync(stats + e->off_g1, e->gvec, sizeof(double) * gstride, cudaMemcpyDeviceToDevice, s));
-    if (full) {
-        const double* Hc1 = chain ? e->Hx : stats + e->off_H;         // Gram weighted by omega^c
-        const double* Dx = chain ? e->Hx + MM : e->Hx;                // distance-weighted Grams, one per input dim
-        const double* gd = e->gvec + gstride;                         // g^{d_i} follow g^mu
-        dim3 grid((unsigned)hm_cdiv(M, 8), (unsigned)Q);
-        gram_dz_kernel<<<grid, 256, 0, s>>>(e->C, e->alpha, e->Zp, e->consts, Hc1, Dx, MM, gd, gstride, stats + e->off_dz, M, Mp, Xd);
+        // ---- transposed projection: g1 = K^T mu and dz = sum_n GK (x - z) per inducing point (tc_bwd.cu)
+        const int nslots = e->nworkers - (e->nworkers % 2);
+        HM_CHECK(hm_tc_proj_bwd(s, e->tk, pa, e->Cb, e->tcinfo, e->colpart, nslots, e->tc_npass));
+        const int ncol = (1 + Xd) * e->Mc + 1;
+        dim3 g1((unsigned)hm_cdiv(ncol, 256), (unsigned)Q);
+        reduce_col_kernel<<<g1, 256, 0, s>>>(e->colpart, nslots, ncol, e->Mc, Mp, Xd, stats + e->off_g1, stats + e->off_dz, nullptr);
         HM_CUDA(cudaGetLastError());
     }
+    if (e->timing) HM_CUDA(cudaEventRecord(e->ev[4], s));
+    // ---- H^1 = sum K^T diag(omega) K  (+ g^mu in a VE step; a full step took it from the transposed projection)
+    HmGramWeights gw;
+    memset(&gw, 0, sizeof(gw));
+    gw.nW = 1; gw.wbase[0] = 1; gw.wdim[0] = -1; gw.wdim[1] = -1;
+    if (!full) { gw.vbase[0] = 0; gw.vdim[0] = -1; gw.nV = 1; }
+    HM_CUDA(cudaMemsetAsync(stats + e->off_H, 0, sizeof(double) * MM, s));
+    HM_CHECK(hm_tc_gram(s, e->tk, pa, e->tcinfo, e->segs_d, e->segoff_d, gw, e->slots, e->nworkers, e->tc_f1, e->tc_f2, e->tc_npass));
+    HM_CHECK(hm_tc_gram_reduce(s, e->slots, e->jobs_d, e->jobslots_d, (int)e->jobs_h.size(), Q, gw, stats + e->off_H, e->gvec, gstride, M, Mp));
+    if (!full) HM_CUDA(cudaMemcpyAsync(stats + e->off_g1, e->gvec, sizeof(double) * gstride, cudaMemcpyDeviceToDevice, s));
     return 0;
 }
 
@@ -782,12 +738,15 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
     A_(KSK, MM); A_(C, MM); A_(tmp, MM); A_(T1, MM); A_(E, MM); A_(tmpE, MM); A_(dLdS, MM); A_(dLdLfull, MM); A_(dLdK, MM);
     A_(Cf, MM);
     e->Cb = nullptr; e->tcinfo = nullptr; e->jobs_d = nullptr; e->segs_d = nullptr; e->segoff_d = nullptr; e->jobslots_d = nullptr;
-    e->slots = nullptr; e->Hx = nullptr; e->gvec = nullptr; e->plan_dirty = true;
+    e->slots = nullptr; e->gvec = nullptr; e->plan_dirty = true;
     e->nworkers = hm_proj_workers(e->prec, e->Mc);
     if (!rc && e->prec == HMOGP_PREC_TC) {
         const char* ev = getenv("HMOGP_TC_NPASS");
         e->tc_npass = ev ? atoi(ev) : 3;
         if (e->tc_npass < 1 || e->tc_npass > 3) e->tc_npass = 3;
+        ev = getenv("HMOGP_TC_FWD_CTAS");            // 2 (default): cta_group::2 CTA pairs; 1: one CTA per SM
+        e->tc_ncta = (ev && atoi(ev) == 1) ? 1 : 2;
+        if (e->nworkers < 2) e->tc_ncta = 1;
         ev = getenv("HMOGP_TC_FLUSH_ROWS");          // level-1 (tensor-core fp32) accumulation window
         e->tc_f1 = (ev ? atoi(ev) : 512) / HM_GRAM_CHUNK;
         if (e->tc_f1 < 1) e->tc_f1 = 1;
@@ -809,7 +768,6 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
         e->nslots_max = e->max_segs;
         A_(jobs_d, nj); A_(segs_d, e->max_segs); A_(segoff_d, e->nworkers + 1); A_(jobslots_d, Q * nj);
         A_(slots, (size_t)e->nslots_max * HM_GRAM_SLOT_DOUBLES);
-        A_(Hx, (size_t)(1 + Xd) * MM);
         A_(gvec, (size_t)HM_GRAM_MAXV * Q * Mp);
         if (!rc && cudaMemcpy(e->jobs_d, e->jobs_h.data(), sizeof(HmGramJob) * nj, cudaMemcpyHostToDevice) != cudaSuccess) rc = HMOGP_ERR_CUDA;
         if (!rc && cudaMemset(e->tcinfo, 0, sizeof(HmTcInfo)) != cudaSuccess) rc = HMOGP_ERR_CUDA;
@@ -935,7 +893,7 @@ int hmogp_step_local(hmogp_engine* e, const hmogp_params* p, int32_t mem_kind, i
     // ---- forward projections
     if (tc) {
         HM_CUDA(cudaMemsetAsync(&e->tcinfo->wmax[0][0], 0, sizeof(unsigned) * 2 * HM_MAXQ, s));
-        HM_CHECK(hm_tc_proj_fwd(s, e->tk, pa, e->Cb, e->tcinfo, what >= HMOGP_WHAT_FULL, e->tc_npass));
+        HM_CHECK(hm_tc_proj_fwd(s, e->tk, pa, e->Cb, e->tcinfo, what >= HMOGP_WHAT_FULL, e->tc_npass, e->tc_ncta));
     } else HM_CHECK(hm_proj_fwd(s, e->prec, e->tk, pa));
     if (e->timing) HM_CUDA(cudaEventRecord(e->ev[2], s));
     // ---- likelihoods
@@ -953,8 +911,7 @@ int hmogp_step_local(hmogp_engine* e, const hmogp_params* p, int32_t mem_kind, i
     if (e->timing) HM_CUDA(cudaEventRecord(e->ev[3], s));
     // ---- backward statistics
     if (what >= HMOGP_WHAT_VE && tc) {
-        if (e->timing) HM_CUDA(cudaEventRecord(e->ev[4], s));
-        HM_CHECK(tc_backward(e, what, stats));
+        HM_CHECK(tc_backward(e, what, stats));                    // records ev[4] between projection and Gram
     } else if (what >= HMOGP_WHAT_VE) {
         HM_CHECK(hm_proj_bwd(s, simt_prec, e->tk, pa, what >= HMOGP_WHAT_FULL));
         const int ncol = (1 + e->Xd) * e->Mc + 1;

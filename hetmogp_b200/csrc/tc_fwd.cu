@@ -17,6 +17,8 @@
 //   warp  16    MMA issuer : one thread, 12 tcgen05.mma (M128 N256 K16) per stage, tcgen05.commit -> mbarriers
 //   warp  17    bulk copy  : cp.async.bulk of the pre-swizzled C_q operand image (hi+lo, 64 KB per stage) from L2
 // Rings: 2 smem stages (96 KB each) full/empty, 2 TMEM accumulators (2 x 256 columns) full/empty.
+#include <string.h>
+
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -26,13 +28,19 @@ namespace {
 constexpr int kRows = 128;   // UMMA M
 constexpr int kNB = 256;     // UMMA N (output columns per job)
 constexpr int kKB = 64;      // inducing points per stage (128 B of fp16 = one swizzle-atom row)
-constexpr int kStages = 2;
 constexpr int kAHalf = kRows * 128;                    // 16 KB : A hi (or lo) image of one stage
-constexpr int kBHalf = kNB * 128;                      // 32 KB : B hi (or lo) image of one stage
-constexpr int kStageBytes = 2 * kAHalf + 2 * kBHalf;   // 96 KB
+constexpr int kBHalf = kNB * 128;                      // 32 KB : B hi (or lo) image of one stage (all 256 rows)
+constexpr int kMaxStages = 3;
+// per-CTA stage: NCTA = 1: A (32 KB) + whole B tile (64 KB), 2 stages;  NCTA = 2 (cta_group::2 pair): A + this CTA's
+// half of the B rows (32 KB), 3 stages
+template <int NCTA> struct FwdCfg {
+    static constexpr int stages = (NCTA == 1) ? 2 : 3;
+    static constexpr int bhalf = kBHalf / NCTA;
+    static constexpr int stage_bytes = 2 * kAHalf + 2 * bhalf;
+};
 constexpr int kGenWarps = 8, kEpiWarps = 8, kMmaWarp = 16;   // + bulk-copy warp 17
 constexpr int kThreads = 576;
-constexpr uint32_t kIdesc = idesc_f16(kRows, kNB);
+
 
 struct TileRef { int t; int64_t row0; int nrows; };
 __device__ __forceinline__ TileRef find_tile(const HmTasks& tk, int64_t tile) {
@@ -98,7 +106,7 @@ __global__ void tc_image_kernel(const double* __restrict__ C, const HmTcInfo* __
 
 // ------------------------------------------------------------------------------------------- forward kernel
 struct FwdBars {
-    uint64_t full[kStages], empty[kStages], tfull[2], tempty[2];
+    uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
     uint32_t tmem_base;
 };
 
@@ -116,11 +124,16 @@ __device__ __forceinline__ void two_sum_add(float& hi, float& lo, float x) {
 // (negated so that the packed loops are pure FADD2 / FFMA2:  K = ex2(-(d.d - bias)))
 template <int XD> struct FwdTab { static constexpr int R = 2 * XD + 3; };
 
-template <int XD>
+template <int XD, int NCTA>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const HmTcInfo* __restrict__ info, int64_t ntiles,
               int hyper, int npass) {
     constexpr int R = FwdTab<XD>::R;
+    constexpr int kStages = FwdCfg<NCTA>::stages, kStageBytes = FwdCfg<NCTA>::stage_bytes, kBH = FwdCfg<NCTA>::bhalf;
+    constexpr uint32_t kIdesc = idesc_f16(kRows * NCTA, kNB);
+    const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;          // 0 = leader of the CTA pair
+    const int64_t nsteps = (ntiles + NCTA - 1) / NCTA;                   // row tiles are taken NCTA at a time
+    const int64_t step0 = blockIdx.x / NCTA, dstep = gridDim.x / NCTA;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // SWIZZLE_128B operand images need a 1024-byte aligned base: align by hand (the launch reserves the slack)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -153,13 +166,14 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
         t8[(2 * XD + 2) * 8] = (m < M) ? (float)pa.alpha[(size_t)q * Mp + m] : 0.f;
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&sb->full[s], kGenWarps + 1); mbar_init(&sb->empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&sb->tfull[b], 1); mbar_init(&sb->tempty[b], kEpiWarps); }
+        // full: generator warps + bulk-copy expect_tx (+ on the leader of a pair: the peer's relay)
+        for (int s = 0; s < kStages; ++s) { mbar_init(&sb->full[s], kGenWarps + 1 + ((NCTA == 2 && rank == 0) ? 1 : 0)); mbar_init(&sb->empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&sb->tfull[b], 1); mbar_init(&sb->tempty[b], kEpiWarps * NCTA); }
         mbar_fence_init();
     }
-    if (warp == kMmaWarp) tmem_alloc(&sb->tmem_base, 512u);
+    if (warp == kMmaWarp) { if (NCTA == 2) tmem_alloc2(&sb->tmem_base, 512u); else tmem_alloc(&sb->tmem_base, 512u); }
     fence_before();
-    __syncthreads();
+    if (NCTA == 2) cluster_sync(); else __syncthreads();
     fence_after();
     const uint32_t tmem_base = sb->tmem_base;
 
@@ -169,8 +183,8 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
         const int rg = warp & 1, cq = warp >> 1;
         const int r0 = rg * 64 + lane, r1 = r0 + 32;
         int stage = 0; uint32_t phase = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const TileRef tr = find_tile(tk, tile);
+        for (int64_t st_ = step0; st_ < nsteps; st_ += dstep) {
+            const TileRef tr = find_tile(tk, st_ * NCTA + rank);
             float2 xh0[XD], xl0[XD], xh1[XD], xl1[XD];
 #pragma unroll
             for (int i = 0; i < XD; ++i) {
@@ -236,8 +250,8 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
         const float inv_pc = pow2i(-(kexp + cexp));      // undo the operand scales of P
         const float inv_s2 = (float)(1.0 / s2);           // scaled squared distance -> |x - z|^2
         uint32_t jc = 0, tcount = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-            const TileRef tr = find_tile(tk, tile);
+        for (int64_t st_ = step0; st_ < nsteps; st_ += dstep, ++tcount) {
+            const TileRef tr = find_tile(tk, st_ * NCTA + rank);
             float xh[XD], xl[XD];
 #pragma unroll
             for (int i = 0; i < XD; ++i) {
@@ -299,7 +313,7 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
                 }
                 fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sb->tempty[buf]);
+                if (lane == 0) { if (NCTA == 2 && rank != 0) mbar_arrive_remote(&sb->tempty[buf], 0); else mbar_arrive(&sb->tempty[buf]); }
             }
             // combine the two column halves of each row: half 1 -> smem -> half 0 -> HBM
             float* xb = xch + (tcount & 1u) * 4 * 128;
@@ -319,49 +333,68 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
             }
         }
     } else if (warp == kMmaWarp) {
-        // ======================================================= MMA issuer (one thread)
-        if (lane == 0) {
+        // ======================================================= MMA issuer (one thread; leader CTA of a pair)
+        if (lane == 0 && rank == 0) {
             int stage = 0; uint32_t phase = 0, jc = 0;
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int64_t st_ = step0; st_ < nsteps; st_ += dstep) {
                 for (int h = 0; h < nhalf; ++h, ++jc) {
                     const uint32_t buf = jc & 1u;
-                    mbar_wait(&sb->tempty[buf], ((jc >> 1) & 1u) ^ 1u);
+                    if (NCTA == 2) mbar_wait_cluster(&sb->tempty[buf], ((jc >> 1) & 1u) ^ 1u);
+                    else mbar_wait(&sb->tempty[buf], ((jc >> 1) & 1u) ^ 1u);
                     fence_after();
                     const uint32_t d_tmem = tmem_base + buf * kNB;
                     for (int kb = 0; kb < nkb; ++kb) {
-                        mbar_wait(&sb->full[stage], phase);
+                        if (NCTA == 2) mbar_wait_cluster(&sb->full[stage], phase);
+                        else mbar_wait(&sb->full[stage], phase);
                         fence_after();
                         const uint32_t sa = smem_u32(stage_base + (size_t)stage * kStageBytes);
                         const uint64_t a_hi = desc_sw128(sa), a_lo = desc_sw128(sa + kAHalf);
-                        const uint64_t b_hi = desc_sw128(sa + 2 * kAHalf), b_lo = desc_sw128(sa + 2 * kAHalf + kBHalf);
+                        const uint64_t b_hi = desc_sw128(sa + 2 * kAHalf), b_lo = desc_sw128(sa + 2 * kAHalf + kBH);
 #pragma unroll
                         for (int ks = 0; ks < kKB / 16; ++ks) {
                             const uint64_t adv = (uint64_t)(ks * 2);   // 32 bytes per K=16 step, in 16-byte units
-                            mma_f16(d_tmem, a_hi + adv, b_hi + adv, kIdesc, (kb | ks) ? 1u : 0u);
-                            if (npass >= 2) mma_f16(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
-                            if (npass >= 3) mma_f16(d_tmem, a_lo + adv, b_hi + adv, kIdesc, 1u);
+                            if (NCTA == 2) {
+                                mma2_f16(d_tmem, a_hi + adv, b_hi + adv, kIdesc, (kb | ks) ? 1u : 0u);
+                                if (npass >= 2) mma2_f16(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
+                                if (npass >= 3) mma2_f16(d_tmem, a_lo + adv, b_hi + adv, kIdesc, 1u);
+                            } else {
+                                mma_f16(d_tmem, a_hi + adv, b_hi + adv, kIdesc, (kb | ks) ? 1u : 0u);
+                                if (npass >= 2) mma_f16(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
+                                if (npass >= 3) mma_f16(d_tmem, a_lo + adv, b_hi + adv, kIdesc, 1u);
+                            }
                         }
-                        commit(&sb->empty[stage]);      // frees the smem stage when these MMAs have read it
+                        if (NCTA == 2) commit2(&sb->empty[stage]); else commit(&sb->empty[stage]);   // frees the smem stage
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
-                    commit(&sb->tfull[buf]);            // accumulator of this job complete
+                    if (NCTA == 2) commit2(&sb->tfull[buf]); else commit(&sb->tfull[buf]);           // accumulator complete
                 }
             }
+        } else if (NCTA == 2 && lane == 0) {
+            // peer CTA of the pair: relay "my operand tiles of this stage are in shared memory" to the leader
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t st_ = step0; st_ < nsteps; st_ += dstep)
+                for (int h = 0; h < nhalf; ++h)
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(&sb->full[stage], phase);
+                        mbar_arrive_remote(&sb->full[stage], 0);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
         }
     } else {
-        // ======================================================= bulk-copy producer (one thread)
+        // ======================================================= bulk-copy producer (one thread): this CTA's rows of B
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int64_t st_ = step0; st_ < nsteps; st_ += dstep) {
                 for (int h = 0; h < nhalf; ++h) {
                     for (int kb = 0; kb < nkb; ++kb) {
                         mbar_wait(&sb->empty[stage], phase ^ 1);
                         uint8_t* dst = stage_base + (size_t)stage * kStageBytes + 2 * kAHalf;
-                        const uint8_t* src = reinterpret_cast<const uint8_t*>(Cb) + ((size_t)(q * nhalf + h) * nkb + kb) * (2 * kBHalf);
-                        mbar_expect_tx(&sb->full[stage], 2 * kBHalf);
-#pragma unroll
-                        for (int part = 0; part < 4; ++part)
-                            bulk_g2s(dst + part * (kBHalf / 2), src + part * (kBHalf / 2), kBHalf / 2, &sb->full[stage]);
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(Cb) + ((size_t)(q * nhalf + h) * nkb + kb) * (2 * kBHalf) + rank * kBH;
+                        mbar_expect_tx(&sb->full[stage], 2 * kBH);
+                        bulk_g2s(dst, src, kBH / 2, &sb->full[stage]);                                   // hi
+                        bulk_g2s(dst + kBH / 2, src + kBH / 2, kBH / 2, &sb->full[stage]);
+                        bulk_g2s(dst + kBH, src + kBHalf, kBH / 2, &sb->full[stage]);                    // lo
+                        bulk_g2s(dst + kBH + kBH / 2, src + kBHalf + kBH / 2, kBH / 2, &sb->full[stage]);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -370,29 +403,50 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
     }
     // ---- teardown
     fence_before();
-    __syncthreads();
-    if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512u);
+    if (NCTA == 2) cluster_sync(); else __syncthreads();
+    if (warp == kMmaWarp) { if (NCTA == 2) tmem_dealloc2(tmem_base, 512u); else tmem_dealloc(tmem_base, 512u); }
 }
 
-size_t fwd_smem_bytes(int Mc, int Xd) {
-    return (size_t)kStages * kStageBytes + sizeof(float) * ((size_t)Mc * (2 * Xd + 3) + 2 * 4 * 128) + sizeof(FwdBars) + 64 + 1024;
+template <int NCTA> size_t fwd_smem_bytes(int Mc, int Xd) {
+    return (size_t)FwdCfg<NCTA>::stages * FwdCfg<NCTA>::stage_bytes + sizeof(float) * ((size_t)Mc * (2 * Xd + 3) + 2 * 4 * 128) +
+           sizeof(FwdBars) + 64 + 1024;
 }
 
-template <int XD>
-int launch_fwd(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const void* Cb, const HmTcInfo* info, int64_t ntiles,
-               bool hyper, int npass) {
-    const size_t smem = fwd_smem_bytes(a.Mc, XD);
+template <int XD, int NCTA>
+int launch_fwd2(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const void* Cb, const HmTcInfo* info, int64_t ntiles,
+                bool hyper, int npass) {
+    const size_t smem = fwd_smem_bytes<NCTA>(a.Mc, XD);
     if (smem > 227 * 1024) {
         hm_set_error("tensor-core projection: M=%d (padded %d) with Xdim=%d needs %zu B of shared memory", a.M, a.Mc, XD, smem);
         return HMOGP_ERR_ARG;
     }
-    HM_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<XD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = tc_fwd_kernel<XD, NCTA>;
+    HM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nw = a.nworkers;
-    if (ntiles < nw) nw = (int)ntiles;
-    dim3 grid((unsigned)nw, (unsigned)a.Q);
-    tc_fwd_kernel<XD><<<grid, kThreads, smem, s>>>(tk, a, reinterpret_cast<const uint16_t*>(Cb), info, ntiles, hyper ? 1 : 0, npass);
+    const int64_t nsteps = (ntiles + NCTA - 1) / NCTA;
+    if (nsteps * NCTA < nw) nw = (int)(nsteps * NCTA);
+    nw -= nw % NCTA;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)nw, (unsigned)a.Q);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (NCTA == 2) ? 1 : 0;
+    HM_CUDA(cudaLaunchKernelEx(&cfg, kern, tk, a, reinterpret_cast<const uint16_t*>(Cb), info, ntiles, hyper ? 1 : 0, npass));
     HM_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int XD>
+int launch_fwd(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const void* Cb, const HmTcInfo* info, int64_t ntiles,
+               bool hyper, int npass, int ncta) {
+    if (ncta == 2) return launch_fwd2<XD, 2>(s, tk, a, Cb, info, ntiles, hyper, npass);
+    return launch_fwd2<XD, 1>(s, tk, a, Cb, info, ntiles, hyper, npass);
 }
 
 }  // namespace
@@ -414,15 +468,15 @@ int hm_tc_prepare(cudaStream_t s, const double* C, const HmConsts* consts, HmTcI
 }
 
 int hm_tc_proj_fwd(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const void* Cb, const HmTcInfo* info, bool hyper,
-                   int npass) {
+                   int npass, int ncta) {
     int64_t ntiles = 0;
     for (int t = 0; t < tk.T; ++t) ntiles += hm_cdiv(tk.count[t], kRows);
     if (ntiles == 0) return 0;
     switch (a.Xdim) {
-        case 1: return launch_fwd<1>(s, tk, a, Cb, info, ntiles, hyper, npass);
-        case 2: return launch_fwd<2>(s, tk, a, Cb, info, ntiles, hyper, npass);
-        case 3: return launch_fwd<3>(s, tk, a, Cb, info, ntiles, hyper, npass);
-        case 4: return launch_fwd<4>(s, tk, a, Cb, info, ntiles, hyper, npass);
+        case 1: return launch_fwd<1>(s, tk, a, Cb, info, ntiles, hyper, npass, ncta);
+        case 2: return launch_fwd<2>(s, tk, a, Cb, info, ntiles, hyper, npass, ncta);
+        case 3: return launch_fwd<3>(s, tk, a, Cb, info, ntiles, hyper, npass, ncta);
+        case 4: return launch_fwd<4>(s, tk, a, Cb, info, ntiles, hyper, npass, ncta);
     }
     hm_set_error("Xdim=%d unsupported", a.Xdim);
     return HMOGP_ERR_ARG;

@@ -5,12 +5,10 @@
 //     g^v_q[i]  = sum_t sum_n v_v[n] K[n,i]
 // w = omega_tq  -> H^1, from which dVE/dS_q = K_uu^-1 H^1 K_uu^-1 (reference: A^T diag(dv) A per output function,
 // /root/reference/hetmogp/svmogp_inf.py:145-148, summed over d with W_dq^2 folded into omega);
-// distance-weighted launches: D^i_q[m, j] = sum_n omega^c[n] s (x_ni - z_mi) K[n,m] K[n,j]  (the weight depends on the
-// output ROW m, which the A-operand generator -- thread = column m of K -- applies for free and without the
-// cancellation of H^{x_i} - z_mi H^1); with H^1 it gives the inducing-input gradient of the K_mn chain
-// (svmogp.py:153-156, GPy RBF.gradients_X) without ever forming dL_dKmn (M x N per (q,d) in the reference,
-// svmogp_inf.py:157-161).  D^i is not symmetric, but D[m,j] - D[j,m] = s (z_j - z_m) H^1[m,j], so the lower
-// block-triangle suffices.  g^mu gives dVE/dm_q (svmogp_inf.py:144).
+// g^mu = K^T mu gives dVE/dm_q (svmogp_inf.py:144); in a full step it comes from tc_bwd.cu together with the
+// inducing-input statistic, so the Gram launch then carries no g-vector.  (The kernel can also weight the A operand
+// by the signed distance s (x_ni - z_mi) of the row it owns -- template flag DIST -- which an earlier revision used to
+// obtain dZ from a second Gram; the transposed projection of tc_bwd.cu replaced it at 0.6x the cost.)
 //
 // MMA: D[i (128 TMEM lanes), j (<=256 columns)] += A[i][n] . B[j][n]^T over n = 32 data rows per stage,
 //   A = 2^wexp w[n] (d_i) K[n, I-block]   B = 2^kexp K[n, J-block]   (split fp16, 3 products).
@@ -473,15 +471,13 @@ int launch_gram3(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const H
     return 0;
 }
 
-// launches the engine issues: (NV = 1) VE step; (NV = 1 + XD) first launch of a full step; (NV = 0) the other Grams
+// launches the engine issues: (NV = 1) VE step (H^1 and g^mu); (NV = 0) full step (H^1 only)
 template <int XD>
 int launch_gram(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const HmTcInfo* info, const HmGramSeg* segs,
                 const int* seg_off, const HmGramWeights& gw, double* slots, int nctas, int f1, int f2, int npass) {
     const bool dist = gw.wdim[0] >= 0;
     if (!dist && gw.nV == 1) return launch_gram3<XD, 1, false>(s, tk, a, info, segs, seg_off, gw, slots, nctas, f1, f2, npass);
-    if (!dist && gw.nV == 1 + XD) return launch_gram3<XD, 1 + XD, false>(s, tk, a, info, segs, seg_off, gw, slots, nctas, f1, f2, npass);
     if (!dist && gw.nV == 0) return launch_gram3<XD, 0, false>(s, tk, a, info, segs, seg_off, gw, slots, nctas, f1, f2, npass);
-    if (dist && gw.nV == 0) return launch_gram3<XD, 0, true>(s, tk, a, info, segs, seg_off, gw, slots, nctas, f1, f2, npass);
     hm_set_error("gram launch: unsupported (dist=%d, nV=%d) for Xdim=%d", (int)dist, gw.nV, XD);
     return HMOGP_ERR_ARG;
 }
