@@ -24,11 +24,11 @@ if os.path.isfile(lp):
         a[1] += v
     tot = sum(a[1] for a in agg.values())
     out.append("# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache serialised: compare SHARES)")
-    out.append("# command: ncu --metrics gpu__time_duration.sum --clock-control none ... python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline")
+    out.append("# command: ncu --metrics gpu__time_duration.sum --clock-control none ... python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline")
     out.append("launches=%d total_ms=%.3f" % (len(data), tot))
     for n, a in sorted(agg.items(), key=lambda x: -x[1][1]):
         out.append("%-72s n=%5d %12.3f ms %6.2f%%" % (n, a[0], a[1], 100 * a[1] / tot))
-rp = os.path.join(ROOT, "gpurun_out", "prof.ncu-rep")
+rp = os.path.join(ROOT, "gpurun_out", sys.argv[2] if len(sys.argv) > 2 else "prof.ncu-rep")
 if os.path.isfile(rp):
     raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
