@@ -269,7 +269,7 @@ def main():
     # (kernel name, algorithmic flops per launch, launches per step) of the N-sized kernels behind each phase timer
     if prec == "tc":
         kern = {"forward_ms": ("tc_fwd_kernel (K_fu build + K_fu C_q on tcgen05 cta_group::2 + row reductions)", work["flops_fwd"], 1),
-                "bwd_gram_ms": ("tc_gram_kernel (H^1 = K_fu^T diag(omega) K_fu on tcgen05, three-level accumulation)", work["flops_gram"], 1)}
+                "bwd_gram_ms": ("tc_gram2_kernel (H^1 = K_fu^T diag(omega) K_fu on tcgen05 cta_group::2, three-level accumulation)", work["flops_gram"], 1)}
         if args.what == "full":
             kern["bwd_proj_ms"] = ("tc_bwd_kernel (transposed projection C_q K_fu^T on tcgen05 cta_group::2 + column sums)", work["flops_bwd_proj"], 1)
     else:
@@ -283,8 +283,8 @@ def main():
     Mc = -(-M // 256) * 256
     issued = {"forward_ms": 3 * 2.0 * work["U"] / (M * M) * Mc * Mc,                       # 3 split-fp16 products, padded M
               "bwd_proj_ms": 3 * 2.0 * work["U"] / (M * M) * Mc * Mc,
-              "bwd_gram_ms": 3 * 2.0 * work["U"] / (M * M) * (Mc * Mc) * 0.625}            # lower block-triangle of 128x256 tiles
-    traffic = {"bwd_gram_ms": 1.03e9, "forward_ms": 3.1e8, "bwd_proj_ms": None}   # dram read+write per launch, ncu --set full (profiles/r1_tc_ncu_summary.txt)
+              "bwd_gram_ms": 3 * 2.0 * work["U"] / (M * M) * (Mc * Mc) * (0.75 if Mc % 256 == 0 else 0.625)}   # lower block-triangle of 256x256 (pair kernel) / 128x256 tiles
+    traffic = {"bwd_gram_ms": 4.65e8, "forward_ms": 3.08e8, "bwd_proj_ms": 4.97e8}   # dram read+write per launch, ncu --set full (profiles/r1_tc2_ncu_summary.txt)
     roofline = {"bound": "tensor", "kernel": kern[dom][0], "achieved": ach, "peak": peaks["tc"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tc"],
                 "traffic": traffic.get(dom) if (prec == "tc" and args.config == "cfg3" and world == 1 and not args.rows) else None,

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhetmogp_b200.so")
+LIB_PATH = os.environ.get("HMOGP_LIB") or os.path.join(_HERE, "lib", "libhetmogp_b200.so")   # HMOGP_LIB: development override
 
 # constants mirrored from include/hetmogp_b200.h
 MEM_HOST, MEM_DEVICE = 0, 1

@@ -137,5 +137,11 @@ int hm_tc_proj_bwd(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const
                    int nslots, int npass);
 int hm_tc_gram(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const HmTcInfo* info, const HmGramSeg* segs,
                const int* seg_off, const HmGramWeights& gw, double* slots, int nctas, int f1, int f2, int npass);
+// CTA-pair Gram (tc_gram2.cu): jobs are 256 x 256 blocks {I = row block, j0, nw = 256}; plan per pair; 2 slots per segment
+#define HM_GRAM2_CHUNK 64
+int hm_tc_gram2(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const HmTcInfo* info, const HmGramSeg* segs,
+                const int* seg_off, int nV, double* slots, int npairs, int f1, int f2, int npass);
+int hm_tc_gram2_reduce(cudaStream_t s, const double* slots, const HmGramJob* jobs, const int2* jobslots, int njobs, int Q, int nV,
+                       double* H, double* g0, int M, int Mp);
 int hm_tc_gram_reduce(cudaStream_t s, const double* slots, const HmGramJob* jobs, const int2* jobslots, int njobs, int Q,
                       const HmGramWeights& gw, double* H, double* g0, int64_t gstride, int M, int Mp);

@@ -365,6 +365,9 @@ struct hmogp_engine {
     void* Cb;              // split-fp16 SW128 operand image of C
     HmTcInfo* tcinfo;
     int tc_npass, tc_f1, tc_f2;   // MMA passes; level-1 window (chunks); level-3 period (windows)
+    int gram2_cost_diag;          // plan cost of a diagonal block job relative to 100 for an off-diagonal one
+    bool gram2;                   // Gram on CTA pairs (tc_gram2.cu): padded M a multiple of 256
+    int gram_chunk;               // data rows per plan chunk
     int tc_ncta;                  // forward kernel: 1 = one CTA per SM, 2 = cta_group::2 CTA pairs
     std::vector<HmGramJob> jobs_h;
     HmGramJob* jobs_d;
@@ -553,15 +556,18 @@ int refresh_tasks(hmogp_engine* e) {
 // tile ("slot").  Slots of one pair are contiguous, so the reduction order is fixed.
 int build_gram_plan(hmogp_engine* e) {
     if (!e->plan_dirty) return 0;
-    const int G = e->nworkers, Q = e->Q, nj = (int)e->jobs_h.size();
+    const int G = e->gram2 ? e->nworkers / 2 : e->nworkers, Q = e->Q, nj = (int)e->jobs_h.size();   // workers: CTAs or CTA pairs
     int64_t NC = 0;
-    for (int t = 0; t < e->T; ++t) NC += hm_cdiv(e->tk.count[t], HM_GRAM_CHUNK);
+    for (int t = 0; t < e->T; ++t) NC += hm_cdiv(e->tk.count[t], e->gram_chunk);
     std::vector<HmGramSeg> segs;
     std::vector<std::vector<HmGramSeg>> per(G);
     std::vector<int2> jobslots((size_t)Q * nj);
     std::vector<int64_t> cost(nj);
     int64_t per_q = 0;
-    for (int j = 0; j < nj; ++j) { cost[j] = e->jobs_h[j].nw + 128; per_q += cost[j]; }   // generated columns per chunk (B + A)
+    for (int j = 0; j < nj; ++j) {   // generated columns per chunk (B + A); pair Gram: one generation serves both on the diagonal
+        cost[j] = e->gram2 ? (e->jobs_h[j].j0 == 256 * e->jobs_h[j].I ? e->gram2_cost_diag : 100) : e->jobs_h[j].nw + 128;
+        per_q += cost[j];
+    }
     const double total = (double)per_q * (double)NC * Q;
     int slot = 0;
     double bs = 0.0;   // tape position of the current block
@@ -633,8 +639,13 @@ int tc_backward(hmogp_engine* e, int what, double* stats) {
     gw.nW = 1; gw.wbase[0] = 1; gw.wdim[0] = -1; gw.wdim[1] = -1;
     if (!full) { gw.vbase[0] = 0; gw.vdim[0] = -1; gw.nV = 1; }
     HM_CUDA(cudaMemsetAsync(stats + e->off_H, 0, sizeof(double) * MM, s));
-    HM_CHECK(hm_tc_gram(s, e->tk, pa, e->tcinfo, e->segs_d, e->segoff_d, gw, e->slots, e->nworkers, e->tc_f1, e->tc_f2, e->tc_npass));
-    HM_CHECK(hm_tc_gram_reduce(s, e->slots, e->jobs_d, e->jobslots_d, (int)e->jobs_h.size(), Q, gw, stats + e->off_H, e->gvec, gstride, M, Mp));
+    if (e->gram2) {
+        HM_CHECK(hm_tc_gram2(s, e->tk, pa, e->tcinfo, e->segs_d, e->segoff_d, gw.nV, e->slots, e->nworkers / 2, e->tc_f1, e->tc_f2, e->tc_npass));
+        HM_CHECK(hm_tc_gram2_reduce(s, e->slots, e->jobs_d, e->jobslots_d, (int)e->jobs_h.size(), Q, gw.nV, stats + e->off_H, e->gvec, M, Mp));
+    } else {
+        HM_CHECK(hm_tc_gram(s, e->tk, pa, e->tcinfo, e->segs_d, e->segoff_d, gw, e->slots, e->nworkers, e->tc_f1, e->tc_f2, e->tc_npass));
+        HM_CHECK(hm_tc_gram_reduce(s, e->slots, e->jobs_d, e->jobslots_d, (int)e->jobs_h.size(), Q, gw, stats + e->off_H, e->gvec, gstride, M, Mp));
+    }
     if (!full) HM_CUDA(cudaMemcpyAsync(stats + e->off_g1, e->gvec, sizeof(double) * gstride, cudaMemcpyDeviceToDevice, s));
     return 0;
 }
@@ -743,21 +754,33 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
     if (!rc && e->prec == HMOGP_PREC_TC) {
         const char* ev = getenv("HMOGP_TC_NPASS");
         e->tc_npass = ev ? atoi(ev) : 3;
-        if (e->tc_npass < 1 || e->tc_npass > 3) e->tc_npass = 3;
+        if (e->tc_npass < 1 || e->tc_npass > 4) e->tc_npass = 3;   // 4: diagnostic (lo x lo product in the pair Gram)
         ev = getenv("HMOGP_TC_FWD_CTAS");            // 2 (default): cta_group::2 CTA pairs; 1: one CTA per SM
         e->tc_ncta = (ev && atoi(ev) == 1) ? 1 : 2;
         if (e->nworkers < 2) e->tc_ncta = 1;
         ev = getenv("HMOGP_TC_FLUSH_ROWS");          // level-1 (tensor-core fp32) accumulation window
-        e->tc_f1 = (ev ? atoi(ev) : 512) / HM_GRAM_CHUNK;
+        const char* eg = getenv("HMOGP_TC_GRAM_CTAS");   // 2 (default): CTA-pair Gram when the padded M is a multiple of 256
+        e->gram2 = !(eg && atoi(eg) == 1) && e->Mc % 256 == 0 && e->nworkers >= 2;
+        e->gram_chunk = e->gram2 ? HM_GRAM2_CHUNK : HM_GRAM_CHUNK;
+        eg = getenv("HMOGP_TC_GRAM_DIAG_COST");
+        e->gram2_cost_diag = eg ? atoi(eg) : 75;
+        e->tc_f1 = (ev ? atoi(ev) : 512) / e->gram_chunk;
         if (e->tc_f1 < 1) e->tc_f1 = 1;
         ev = getenv("HMOGP_TC_FLUSH3_ROWS");         // rows between fp64 flushes
-        e->tc_f2 = (ev ? atoi(ev) : 16384) / (e->tc_f1 * HM_GRAM_CHUNK);
+        e->tc_f2 = (ev ? atoi(ev) : 16384) / (e->tc_f1 * e->gram_chunk);
         if (e->tc_f2 < 1) e->tc_f2 = 1;
         unsigned short* cb = nullptr;
         rc = dalloc(e, &cb, hm_tc_image_elems(e->Mc, e->Q));
         e->Cb = cb;
         A_(tcinfo, 1);
         // output tiles of the lower block-triangle of an Mc x Mc Gram: rows [128 I, +128) x columns in pieces of <= 256
+        if (e->gram2) {   // pair Gram: 256 x 256 blocks of the lower block-triangle
+            for (int I = 0; I < e->Mc / 256; ++I)
+                for (int j0 = 0; j0 <= I * 256; j0 += 256) {
+                    HmGramJob jb; jb.I = I; jb.j0 = j0; jb.nw = 256;
+                    e->jobs_h.push_back(jb);
+                }
+        } else
         for (int I = 0; I < e->Mc / 128; ++I)
             for (int j0 = 0; j0 < (I + 1) * 128; j0 += 256) {
                 HmGramJob jb; jb.I = I; jb.j0 = j0; jb.nw = ((I + 1) * 128 - j0) < 256 ? ((I + 1) * 128 - j0) : 256;
@@ -767,7 +790,7 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
         e->max_segs = (int)(e->nworkers + Q * nj + 8);
         e->nslots_max = e->max_segs;
         A_(jobs_d, nj); A_(segs_d, e->max_segs); A_(segoff_d, e->nworkers + 1); A_(jobslots_d, Q * nj);
-        A_(slots, (size_t)e->nslots_max * HM_GRAM_SLOT_DOUBLES);
+        A_(slots, (size_t)e->nslots_max * (e->gram2 ? 2 : 1) * HM_GRAM_SLOT_DOUBLES);
         A_(gvec, (size_t)HM_GRAM_MAXV * Q * Mp);
         if (!rc && cudaMemcpy(e->jobs_d, e->jobs_h.data(), sizeof(HmGramJob) * nj, cudaMemcpyHostToDevice) != cudaSuccess) rc = HMOGP_ERR_CUDA;
         if (!rc && cudaMemset(e->tcinfo, 0, sizeof(HmTcInfo)) != cudaSuccess) rc = HMOGP_ERR_CUDA;

@@ -72,6 +72,8 @@ def scale(cfg, N, ref_prec="fp64", whats=("full",)):
     print("PARITY %s N=%d tc vs %s: elbo=%.12g ref=%.12g rel=%.2e  " % (cfg, N, ref_prec, out["log_marginal"][0, 0],
                                                                       o["log_marginal"][0, 0], e) +
           "  ".join("%s=%.2e" % (k, pu.relerr(out[k], o[k])) for k in GRADS))
+    if "ve" in outs:
+        print("PARITY %s N=%d tc ve vs %s: " % (cfg, N, ref_prec) + "  ".join("%s=%.2e" % (k, pu.relerr(outs["ve"][k], o[k])) for k in ("dL_dmu_u", "dL_dL_u")))
     print("D_RBF tc ", np.array2string(out["d_rbf"].ravel(), precision=6), " ref", np.array2string(o["d_rbf"].ravel(), precision=6))
     if os.environ.get("TC_CHECK_FP32"):
         e32 = pu.make_engine(prob, "fp32")
