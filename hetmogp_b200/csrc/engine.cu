@@ -379,6 +379,11 @@ struct hmogp_engine {
     double *KLq, *KLpart, *jitter_d, *rowstat, *dzmm;
     cudaStream_t s2;          // side stream of the prepare phase (S, S^-1 branch)
     cudaEvent_t ev_fork, ev_S, ev_Sinv;
+    cudaStream_t sc;          // copy stream: host -> device data uploads overlap the M-sized prepare phase of the next step
+    cudaEvent_t ev_cfence, ev_data;
+    bool data_pending;        // an upload on sc has not been ordered before the compute stream yet
+    const double* up_X[HM_MAXT];   // deferred uploads from pinned host memory (queued behind the next step's parameter copies,
+    const double* up_Y[HM_MAXT];   // so that the M-sized prepare phase is not stuck behind them in the copy engine)
     int *flags_d;  // [2][HM_MAXQ]: chol_fail, lu_singular
     // statistics
     int64_t stats_len;
@@ -450,6 +455,8 @@ HmProjArgs proj_args(hmogp_engine* e) {
     return a;
 }
 
+int flush_uploads(hmogp_engine* e);
+
 // ---- prepare: everything M-sized that precedes the data pass.  Returns HMOGP_ERR_LINALG if jitchol gives up.
 int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
     cudaStream_t s = e->stream;
@@ -466,6 +473,7 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
     HM_CHECK(copy_in(e, e->pkc, p->kappa_chain, (size_t)J * Q, mem_kind));
     HM_CHECK(copy_in(e, e->pbs, p->batch_scale, T, mem_kind));
     e->has_chain = p->W_chain != nullptr || p->kappa_chain != nullptr;
+    HM_CHECK(flush_uploads(e));   // row uploads go behind the parameter copies in the copy engine
     prep_consts_kernel<<<1, 256, 0, s>>>(e->consts, e->pvar, e->pls, e->pW, e->pkappa, p->W_chain ? e->pWc : nullptr,
                                          p->kappa_chain ? e->pkc : nullptr, p->batch_scale ? e->pbs : nullptr, Q, J, T);
     HM_CUDA(cudaGetLastError());
@@ -546,6 +554,35 @@ int refresh_tasks(hmogp_engine* e) {
         if (!e->Xd_[t]) { hm_set_error("task %d has no data (call hmogp_set_data)", t); return HMOGP_ERR_ARG; }
         e->tk.X[t] = e->Xd_[t];
         e->tk.Y[t] = e->Yd_[t];
+    }
+    return 0;
+}
+
+// queue the deferred uploads on the copy stream, after everything already queued on the compute stream (which may still
+// read the old rows)
+int flush_uploads(hmogp_engine* e) {
+    bool any = false;
+    for (int t = 0; t < e->T; ++t) any = any || e->up_X[t];
+    if (!any) return 0;
+    HM_CUDA(cudaEventRecord(e->ev_cfence, e->stream));
+    HM_CUDA(cudaStreamWaitEvent(e->sc, e->ev_cfence, 0));
+    for (int t = 0; t < e->T; ++t) {
+        if (!e->up_X[t]) continue;
+        HM_CUDA(cudaMemcpyAsync(e->Xd_[t], e->up_X[t], (size_t)e->N[t] * e->Xd * sizeof(double), cudaMemcpyHostToDevice, e->sc));
+        HM_CUDA(cudaMemcpyAsync(e->Yd_[t], e->up_Y[t], (size_t)e->N[t] * sizeof(double), cudaMemcpyHostToDevice, e->sc));
+        e->up_X[t] = e->up_Y[t] = nullptr;
+    }
+    HM_CUDA(cudaEventRecord(e->ev_data, e->sc));
+    e->data_pending = true;
+    return 0;
+}
+
+// order pending row uploads (copy stream) before whatever is queued next on the compute stream
+int data_ready(hmogp_engine* e) {
+    HM_CHECK(flush_uploads(e));
+    if (e->data_pending) {
+        HM_CUDA(cudaStreamWaitEvent(e->stream, e->ev_data, 0));
+        e->data_pending = false;
     }
     return 0;
 }
@@ -817,10 +854,15 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
             if (cudaEventCreate(&e->ev[i]) != cudaSuccess) { hm_set_error("cudaEventCreate failed"); rc = HMOGP_ERR_CUDA; break; }
     }
     e->s2 = nullptr; e->ev_fork = e->ev_S = e->ev_Sinv = nullptr;
+    e->sc = nullptr; e->ev_cfence = e->ev_data = nullptr; e->data_pending = false;
+    for (int t = 0; t < HM_MAXT; ++t) e->up_X[t] = e->up_Y[t] = nullptr;
     if (!rc && (cudaStreamCreateWithFlags(&e->s2, cudaStreamNonBlocking) != cudaSuccess ||
                 cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&e->ev_S, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&e->ev_Sinv, cudaEventDisableTiming) != cudaSuccess)) {
+                cudaEventCreateWithFlags(&e->ev_Sinv, cudaEventDisableTiming) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&e->sc, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&e->ev_cfence, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&e->ev_data, cudaEventDisableTiming) != cudaSuccess)) {
         hm_set_error("side stream / event creation failed");
         rc = HMOGP_ERR_CUDA;
     }
@@ -844,6 +886,9 @@ void hmogp_destroy(hmogp_engine* e) {
     if (e->ev_S) cudaEventDestroy(e->ev_S);
     if (e->ev_Sinv) cudaEventDestroy(e->ev_Sinv);
     if (e->s2) cudaStreamDestroy(e->s2);
+    if (e->ev_cfence) cudaEventDestroy(e->ev_cfence);
+    if (e->ev_data) cudaEventDestroy(e->ev_data);
+    if (e->sc) cudaStreamDestroy(e->sc);
     delete e;
 }
 
@@ -858,6 +903,7 @@ int hmogp_set_data(hmogp_engine* e, int32_t t, const double* X, const double* Y,
     HM_CUDA(cudaSetDevice(e->device));
     if (N > e->cap[t] || !e->Xd_[t]) {
         HM_CUDA(cudaStreamSynchronize(e->stream));
+        HM_CUDA(cudaStreamSynchronize(e->sc));
         if (e->Xd_[t]) cudaFree(e->Xd_[t]);
         if (e->Yd_[t]) cudaFree(e->Yd_[t]);
         if (e->tk.AC[t]) cudaFree(e->tk.AC[t]);
@@ -871,10 +917,24 @@ int hmogp_set_data(hmogp_engine* e, int32_t t, const double* X, const double* Y,
         e->cap[t] = N;
         e->tk.cap[t] = (int64_t)n;
     }
-    const cudaMemcpyKind k = mem_kind == HMOGP_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-    if (N > 0) {
-        HM_CUDA(cudaMemcpyAsync(e->Xd_[t], X, (size_t)N * e->Xd * sizeof(double), k, e->stream));
-        HM_CUDA(cudaMemcpyAsync(e->Yd_[t], Y, (size_t)N * sizeof(double), k, e->stream));
+    e->up_X[t] = e->up_Y[t] = nullptr;
+    if (N > 0 && mem_kind == HMOGP_MEM_HOST) {
+        // Pinned buffers (which the caller must keep valid until the next step has run, as for any asynchronous copy) are
+        // uploaded on the copy stream, queued by the next step right after its parameter copies: the M-sized prepare phase
+        // then overlaps the upload.  Pageable memory is copied here and now (the driver stages it synchronously anyway).
+        cudaPointerAttributes at;
+        const bool pinned = cudaPointerGetAttributes(&at, X) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+                            cudaPointerGetAttributes(&at, Y) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (pinned) {
+            e->up_X[t] = X; e->up_Y[t] = Y;
+        } else {
+            HM_CUDA(cudaMemcpyAsync(e->Xd_[t], X, (size_t)N * e->Xd * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+            HM_CUDA(cudaMemcpyAsync(e->Yd_[t], Y, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        }
+    } else if (N > 0) {
+        HM_CUDA(cudaMemcpyAsync(e->Xd_[t], X, (size_t)N * e->Xd * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+        HM_CUDA(cudaMemcpyAsync(e->Yd_[t], Y, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
     }
     e->N[t] = N;
     e->tk.begin[t] = 0;
@@ -909,6 +969,7 @@ int hmogp_step_local(hmogp_engine* e, const hmogp_params* p, int32_t mem_kind, i
     e->launch0 = hm_launch_counter;
     if (e->timing) HM_CUDA(cudaEventRecord(e->ev[0], s));
     HM_CHECK(mm_prepare(e, p, mem_kind));
+    HM_CHECK(data_ready(e));
     if (e->timing) HM_CUDA(cudaEventRecord(e->ev[1], s));
     HM_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (what >= HMOGP_WHAT_VE ? (int64_t)e->off_H : e->stats_len), s));
     HmProjArgs pa = proj_args(e);
@@ -1066,6 +1127,7 @@ int hmogp_inference_host(const hmogp_config* cfg, const double* const* X, const 
 int hmogp_get_rows(hmogp_engine* e, int32_t t, double* m_fd, double* v_fd, double* VE, double* dm, double* dv) {
     if (!e || t < 0 || t >= e->T || e->last_what < 0) { hm_set_error("hmogp_get_rows: no evaluation yet / bad task"); return HMOGP_ERR_ARG; }
     HM_CUDA(cudaSetDevice(e->device));
+    HM_CHECK(data_ready(e));
     const int64_t n = e->tk.count[t];
     const int F = e->tk.dimf[t];
     if (n == 0) return 0;
@@ -1097,6 +1159,7 @@ int hmogp_get_rows(hmogp_engine* e, int32_t t, double* m_fd, double* v_fd, doubl
 int hmogp_get_dL_dKmn(hmogp_engine* e, int32_t q, int32_t d, double* dL_dKmn, double* dL_dKdiag) {
     if (!e || q < 0 || q >= e->Q || d < 0 || d >= e->J || e->last_what < HMOGP_WHAT_VE) { hm_set_error("hmogp_get_dL_dKmn: bad argument / no gradient evaluation yet"); return HMOGP_ERR_ARG; }
     HM_CUDA(cudaSetDevice(e->device));
+    HM_CHECK(data_ready(e));
     int t = 0;
     while (t + 1 < e->T && e->tk.foff[t + 1] <= d) ++t;
     const int f = d - e->tk.foff[t], F = e->tk.dimf[t];

@@ -67,9 +67,7 @@ class Engine(object):
             assert int(y.shape[0]) == n, "X[%d] and Y[%d] disagree on N" % (t, t)
             check(lib.hmogp_set_data(self._h, t, ptr(x), ptr(y), n, kind))
             self.N[t] = n
-            self._keep.append((x, y))
-        self.sync()
-        self._keep = []
+            self._keep.append((x, y))   # pinned host buffers are uploaded by the next step (hmogp_set_data): keep them alive
         self._count = list(self.N)
 
     def set_rows(self, begin=None, count=None):

@@ -104,17 +104,25 @@ CASES = {
     "pad_m300": dict(liks=[("Gaussian", 0.5), ("Bernoulli",), ("Poisson",)], N=2500, M=300, Q=3, Xdim=1),
     "ragged_x2": dict(liks=[("Categorical", 4), ("Gaussian", 0.5)], N=[1500, 1], M=100, Q=2, Xdim=2, kappa_scale=1.0),
     "m513": dict(liks=[("Bernoulli",)], N=700, M=513, Q=1, Xdim=1),
+    # padded M a multiple of 256: the CTA-pair Gram kernel (tc_gram2.cu) with Xdim = 2 / 3, ragged tasks, three block rows
+    "pair_m200_x2": dict(liks=[("Gamma",), ("Beta",), ("Gaussian", 0.5)], N=[1500, 700, 3], M=200, Q=2, Xdim=2),
+    "pair_m700_x3": dict(liks=[("Bernoulli",), ("Poisson",)], N=[900, 130], M=700, Q=1, Xdim=3),
 }
 
 
 @pytest.mark.parametrize("precision", ["fp64", "fp32", "tc"])
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_engine_matches_oracle(name, precision):
-    """Padding edges (M not a multiple of the tile, Mp != Mc), ragged tasks (N_t = 1), Xdim = 2."""
+    """Padding edges (M not a multiple of the tile, Mp != Mc), ragged tasks (N_t = 1), Xdim = 2 / 3, both Gram kernels."""
     c = dict(CASES[name])
     prob = synth.make_problem(c.pop("liks"), c.pop("N"), c.pop("M"), c.pop("Q"), Xdim=c.pop("Xdim"), seed=7, **c)
     err, out, o = pu.compare(prob, precision)
-    tol = TOL[precision]
+    tol = dict(TOL[precision])
+    if name == "pair_m200_x2" and precision == "tc":
+        # Gamma / Beta rows with posterior variances down to 1e-3 of the prior: v = k_nn + c_n cancels, the split-fp16
+        # forward gives v to 1e-2 relative on those rows and dW (a signed sum over rows) to 1e-2; fp32 SIMT: 2e-3.
+        # Measured identically with either Gram kernel (HMOGP_TC_GRAM_CTAS=1).
+        tol["grad"] = 2e-2
     assert err["elbo"] < tol["elbo"]
     for k in GRADS:
         assert err[k] < tol["grad"], (k, err[k])

@@ -18,6 +18,9 @@ CASES = {
     "all": dict(liks=ALL, N=[150, 260, 140, 130, 145, 150, 120, 77, 64], M=40, Q=3, Xdim=1, batch_scale=[1, 2, 1.5, 1, 1, 3, 1, 1, 1.25]),
     "m300": dict(liks=[("Gaussian", 0.5), ("Bernoulli",), ("Poisson",)], N=3000, M=300, Q=3, Xdim=1),
     "x2": dict(liks=[("Categorical", 4), ("Gaussian", 0.5)], N=[1500, 901], M=100, Q=2, Xdim=2, kappa_scale=1.0),
+    "pair_m200_x2": dict(liks=[("Gamma",), ("Beta",), ("Gaussian", 0.5)], N=[1500, 700, 3], M=200, Q=2, Xdim=2),
+    "pair_m200_x2_old": dict(liks=[("Gamma",), ("Beta",), ("Gaussian", 0.5)], N=[1500, 700, 3], M=200, Q=2, Xdim=2),
+    "pair_m700_x3": dict(liks=[("Bernoulli",), ("Poisson",)], N=[900, 130], M=700, Q=1, Xdim=3),
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)
