@@ -132,7 +132,10 @@ int hmogp_generate_metadata(int32_t T, const hmogp_lik_desc* liks, int64_t* task
 int hmogp_create(const hmogp_config* cfg, hmogp_engine** out);
 void hmogp_destroy(hmogp_engine* e);
 int hmogp_set_stream(hmogp_engine* e, void* cuda_stream);
-/* Copy one task's rows to the device (resident shard).  X [N,Xdim], Y [N] (labels stored as floats). */
+/* Copy one task's rows to the device (resident shard).  X [N,Xdim], Y [N] (labels stored as floats).
+ * HMOGP_MEM_HOST with pinned (page-locked) buffers: the upload is queued by the next step call, behind its parameter
+ * copies, and overlaps the M-sized prepare phase; the buffers must stay valid until that step has run.  Pageable host
+ * memory is copied inside this call. */
 int hmogp_set_data(hmogp_engine* e, int32_t t, const double* X, const double* Y, int64_t N, int32_t mem_kind);
 /* Restrict the data term to rows [begin[t], begin[t]+count[t]) of each task (minibatch slice,
  * util.py:52-72 / per-rank shard); NULL = all rows. */
