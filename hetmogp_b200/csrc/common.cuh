@@ -81,7 +81,14 @@ struct HmTcInfo {
 // Row-major, leading dimension ld, batch of Q matrices with stride sQ.
 int hm_dgemm(cudaStream_t s, bool ta, bool tb, int M, int N, int K, double alpha, const double* A, int lda, int64_t sA,
              const double* B, int ldb, int64_t sB, double beta, double* C, int ldc, int64_t sC, int batch,
-             int nsub = 1, int64_t subA = 0, int64_t subB = 0, int64_t subC = 0, bool lower_only = false);
+             int nsub = 1, int64_t subA = 0, int64_t subB = 0, int64_t subC = 0, int flags = 0);
+enum {
+    HM_GEMM_LOWER = 1,    // only the 64x64 tiles on or below the block diagonal are computed
+    HM_GEMM_MIRROR = 2,   // symmetric product: lower tiles computed, their transposes written too
+    HM_GEMM_K_GE = 4,     // op(A)[i,k] = 0 for k < i and op(B)[k,j] = 0 for k < j   (X^T X, X lower-triangular)
+    HM_GEMM_K_LE = 8,     // op(A)[i,k] = 0 for k > i and op(B)[k,j] = 0 for k > j   (L L^T)
+    HM_GEMM_KB_GE = 16    // op(B)[k,j] = 0 for k < j                                (. L, L lower-triangular)
+};
 int hm_cholesky(cudaStream_t s, double* A, int Mp, int64_t sQ, int Q, int* flags);       // in place, lower
 int hm_tri_inverse(cudaStream_t s, const double* L, double* X, double* tmp, int Mp, int64_t sQ, int Q);
 int hm_build_kuu(cudaStream_t s, const double* Zp, const HmConsts* c, const double* jitter, double* Kuu, int M, int Mp,

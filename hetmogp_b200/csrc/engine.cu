@@ -134,12 +134,21 @@ __global__ void kl_finish_kernel(const double* KLpart, int nblk, double* KLq, in
 }
 
 // ---- statistic reducers (deterministic: fixed summation order)
+// one block per statistic: strided partial sums, then a fixed-order tree (deterministic)
 __global__ void reduce_lik_kernel(const double* partials, int nblocks, int nstat, double* stats, int t, int T, int J, int Q,
                                   int foff, int dimf, int off_sdv, int off_sma, int off_svc, int off_dls) {
-    const int i = threadIdx.x;
-    if (i >= nstat) return;
+    const int i = blockIdx.x;
+    __shared__ double sh[128];
     double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += partials[(int64_t)b * nstat + i];
+    for (int b = threadIdx.x; b < nblocks; b += 128) s += partials[(int64_t)b * nstat + i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 64; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    s = sh[0];
     const int nbase = 2 + dimf * (1 + 2 * Q);
     if (i == 0) stats[t] = s;
     else if (i == 1) stats[T + t] = s;
@@ -266,13 +275,18 @@ __global__ void assemble_scalar_kernel(AssembleArgs a) {
         a.dW[e] = c->W[d][q] * sdv[d] + sma[e] + 2.0 * c->W[d][q] * svc[e];
         a.dkappa[e] = sdv[d];
     }
-    if (tid < a.Q) {
-        const int q = tid;
+    if (tid < 32 * a.Q) {   // one warp per latent (Q <= 8 = blockDim / 32): lane-strided sums + a fixed shuffle tree
+        const int q = tid >> 5, lane = tid & 31;
         double s0 = 0.0, s1 = 0.0;
-        for (int m = 0; m < a.M; ++m) {
+        for (int m = lane; m < a.M; m += 32) {
             s0 += a.rowstat[((int64_t)q * a.Mp + m) * 2 + 0];
             s1 += a.rowstat[((int64_t)q * a.Mp + m) * 2 + 1];
         }
+        for (int w = 16; w > 0; w >>= 1) {
+            s0 += __shfl_down_sync(0xffffffffu, s0, w);
+            s1 += __shfl_down_sync(0xffffffffu, s1, w);
+        }
+        if (lane != 0) return;
         double dvar = s0 / c->var[q];   // update_gradients_full(dL_dKmm, Z_q)   svmogp.py:116
         double dls = s1 / c->ls[q];
         double kmn = 0.0, kd = 0.0;
@@ -456,6 +470,12 @@ HmProjArgs proj_args(hmogp_engine* e) {
 }
 
 int flush_uploads(hmogp_engine* e);
+#ifdef HM_DEBUG_SKIP
+static int dbg_skip() { static int v = -1; if (v < 0) { const char* e = getenv("HMOGP_DEBUG_SKIP"); v = e ? atoi(e) : 0; } return v; }
+#define HM_SKIP(bit) (dbg_skip() & (bit))
+#else
+#define HM_SKIP(bit) 0
+#endif
 
 // ---- prepare: everything M-sized that precedes the data pass.  Returns HMOGP_ERR_LINALG if jitchol gives up.
 int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
@@ -486,10 +506,10 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
     cudaStream_t s2 = e->s2;
     HM_CUDA(cudaEventRecord(e->ev_fork, s));
     HM_CUDA(cudaStreamWaitEvent(s2, e->ev_fork, 0));
-    HM_CHECK(hm_dgemm(s2, false, true, Mp, Mp, Mp, 1.0, e->Lu, Mp, sQ, e->Lu, Mp, sQ, 0.0, e->S, Mp, sQ, Q));
+    HM_CHECK(hm_dgemm(s2, false, true, Mp, Mp, Mp, 1.0, e->Lu, Mp, sQ, e->Lu, Mp, sQ, 0.0, e->S, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR | HM_GEMM_K_LE));
     HM_CUDA(cudaEventRecord(e->ev_S, s2));
-    HM_CHECK(hm_tri_inverse(s2, e->Lu, e->LuInv, e->T1, Mp, sQ, Q));
-    HM_CHECK(hm_dgemm(s2, true, false, Mp, Mp, Mp, 1.0, e->LuInv, Mp, sQ, e->LuInv, Mp, sQ, 0.0, e->Sinv, Mp, sQ, Q));
+    if (!HM_SKIP(4)) HM_CHECK(hm_tri_inverse(s2, e->Lu, e->LuInv, e->T1, Mp, sQ, Q));
+    HM_CHECK(hm_dgemm(s2, true, false, Mp, Mp, Mp, 1.0, e->LuInv, Mp, sQ, e->LuInv, Mp, sQ, 0.0, e->Sinv, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR | HM_GEMM_K_GE));
     HM_CUDA(cudaEventRecord(e->ev_Sinv, s2));
     // K_uu, jitchol (util.py:197-198): no jitter unless the plain factorisation fails; then var*1e-6 * 10^k, k<5
     double var_h[HM_MAXQ];
@@ -500,11 +520,12 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
         HM_CHECK(hm_build_kuu(s, e->Zp, e->consts, e->jitter_d, e->Kuu, M, Mp, Xd, Q));
         HM_CUDA(cudaMemcpyAsync(e->Luu, e->Kuu, sizeof(double) * sQ * Q, cudaMemcpyDeviceToDevice, s));
         HM_CUDA(cudaMemsetAsync(e->flags_d, 0, sizeof(int) * 2 * HM_MAXQ, s));
-        HM_CHECK(hm_cholesky(s, e->Luu, Mp, sQ, Q, e->flags_d));
+        if (!HM_SKIP(1)) HM_CHECK(hm_cholesky(s, e->Luu, Mp, sQ, Q, e->flags_d));
         int fl[HM_MAXQ];
         HM_CUDA(cudaMemcpyAsync(fl, e->flags_d, sizeof(int) * Q, cudaMemcpyDeviceToHost, s));
-        HM_CUDA(cudaStreamSynchronize(s));
+        if (!HM_SKIP(64)) HM_CUDA(cudaStreamSynchronize(s));
         bool any = false;
+        if (HM_SKIP(64)) for (int q = 0; q < Q; ++q) fl[q] = 0;
         for (int q = 0; q < Q; ++q) any = any || fl[q];
         if (!any) break;
         if (attempt >= 5) {
@@ -520,8 +541,8 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
             if (fl[q]) e->jitter_h[q] = (e->jitter_h[q] == 0.0) ? var_h[q] * 1e-6 : e->jitter_h[q] * 10.0;
     }
     // K_uu^-1 = Luu^-T Luu^-1   (dpotri, util.py:199)
-    HM_CHECK(hm_tri_inverse(s, e->Luu, e->LuuInv, e->tmp, Mp, sQ, Q));
-    HM_CHECK(hm_dgemm(s, true, false, Mp, Mp, Mp, 1.0, e->LuuInv, Mp, sQ, e->LuuInv, Mp, sQ, 0.0, e->Ki, Mp, sQ, Q));
+    if (!HM_SKIP(2)) HM_CHECK(hm_tri_inverse(s, e->Luu, e->LuuInv, e->tmp, Mp, sQ, Q));
+    HM_CHECK(hm_dgemm(s, true, false, Mp, Mp, Mp, 1.0, e->LuuInv, Mp, sQ, e->LuuInv, Mp, sQ, 0.0, e->Ki, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR | HM_GEMM_K_GE));
     // alpha = Ki m ; SK = S Ki ; KSK = Ki S Ki ; C = KSK - Ki
     {
         dim3 grid((unsigned)hm_cdiv(Mp, 8), (unsigned)Q);
@@ -529,8 +550,8 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
         HM_CUDA(cudaGetLastError());
     }
     HM_CUDA(cudaStreamWaitEvent(s, e->ev_S, 0));
-    HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->S, Mp, sQ, e->Ki, Mp, sQ, 0.0, e->SK, Mp, sQ, Q));
-    HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->Ki, Mp, sQ, e->SK, Mp, sQ, 0.0, e->KSK, Mp, sQ, Q));
+    if (!HM_SKIP(8)) HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->S, Mp, sQ, e->Ki, Mp, sQ, 0.0, e->SK, Mp, sQ, Q));
+    if (!HM_SKIP(8)) HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->Ki, Mp, sQ, e->SK, Mp, sQ, 0.0, e->KSK, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR));
     {
         const int64_t n = sQ * Q;
         make_c_kernel<<<(unsigned)hm_cdiv(n, 256), 256, 0, s>>>(e->KSK, e->Ki, e->C, e->Cf, n);
@@ -540,12 +561,12 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
     {
         const int nblk = 48;   // <= 64 (KLpart)
         dim3 grid((unsigned)nblk, (unsigned)Q);
-        kl_kernel<<<grid, 256, 0, s>>>(e->Ki, e->S, e->Sinv, e->mp, e->alpha, e->Luu, e->Lu, e->KLpart, e->flags_d + HM_MAXQ, M, Mp);
+        if (!HM_SKIP(16)) kl_kernel<<<grid, 256, 0, s>>>(e->Ki, e->S, e->Sinv, e->mp, e->alpha, e->Luu, e->Lu, e->KLpart, e->flags_d + HM_MAXQ, M, Mp);
         HM_CUDA(cudaGetLastError());
         kl_finish_kernel<<<1, Q, 0, s>>>(e->KLpart, nblk, e->KLq, M);
         HM_CUDA(cudaGetLastError());
     }
-    if (e->prec == HMOGP_PREC_TC) HM_CHECK(hm_tc_prepare(s, e->C, e->consts, e->tcinfo, e->Cb, M, Mp, e->Mc, Q));
+    if (e->prec == HMOGP_PREC_TC && !HM_SKIP(32)) HM_CHECK(hm_tc_prepare(s, e->C, e->consts, e->tcinfo, e->Cb, M, Mp, e->Mc, Q));
     return 0;
 }
 
@@ -988,7 +1009,7 @@ int hmogp_step_local(hmogp_engine* e, const hmogp_params* p, int32_t mem_kind, i
                              e->lik_max_blocks, &nb, nullptr, nullptr, nullptr, nullptr, nullptr, tc ? e->tcinfo : nullptr,
                              what >= HMOGP_WHAT_FULL));
         const int nstat = 2 + e->tk.dimf[t] * (1 + 2 * e->Q) + (tc ? e->Q : 0);
-        reduce_lik_kernel<<<1, 128, 0, s>>>(e->lik_part, nb, nstat, stats, t, e->T, e->J, e->Q, e->tk.foff[t], e->tk.dimf[t],
+        reduce_lik_kernel<<<nstat, 128, 0, s>>>(e->lik_part, nb, nstat, stats, t, e->T, e->J, e->Q, e->tk.foff[t], e->tk.dimf[t],
                                             e->off_sdv, e->off_sma, e->off_svc, e->off_dls);
         HM_CUDA(cudaGetLastError());
     }
@@ -1038,11 +1059,11 @@ int hmogp_step_finish(hmogp_engine* e, const double* stats_dev, hmogp_grads* g, 
         dgemv_kernel<<<gv, 256, 0, s>>>(e->Ki, g1, e->kg, Mp);  // Ki g1  (svmogp_inf.py:144)
         HM_CUDA(cudaGetLastError());
         HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->Ki, Mp, sQ, H, Mp, sQ, 0.0, e->T1, Mp, sQ, Q));
-        HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->T1, Mp, sQ, e->Ki, Mp, sQ, 0.0, e->E, Mp, sQ, Q));  // E = Ki H Ki
+        HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->T1, Mp, sQ, e->Ki, Mp, sQ, 0.0, e->E, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR));  // E = Ki H Ki
         const int64_t n = sQ * Q;
         dlds_kernel<<<(unsigned)hm_cdiv(n, 256), 256, 0, s>>>(e->E, e->Ki, e->Sinv, e->dLdS, n);
         HM_CUDA(cudaGetLastError());
-        HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->dLdS, Mp, sQ, e->Lu, Mp, sQ, 0.0, e->dLdLfull, Mp, sQ, Q));
+        HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->dLdS, Mp, sQ, e->Lu, Mp, sQ, 0.0, e->dLdLfull, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_LOWER | HM_GEMM_KB_GE));   // only the lower triangle is read
         if (what >= HMOGP_WHAT_FULL || g->dL_dKmm) {
             HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->E, Mp, sQ, e->SK, Mp, sQ, 0.0, e->tmpE, Mp, sQ, Q));  // E S Ki
             dim3 gk((unsigned)hm_cdiv(Mp, 128), (unsigned)Mp, (unsigned)Q);

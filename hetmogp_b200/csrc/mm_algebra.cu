@@ -10,57 +10,84 @@
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------------ GEMM
-// C = alpha * op(A) op(B) + beta * C ; 64x64x16 tiles, 256 threads, 4x4 register tile.  Bounds-checked.
+// C = alpha * op(A) op(B) + beta * C ; 64x64x16 tiles, 256 threads, 4x4 register tile; the next k-tile is fetched from
+// global memory (128-bit loads) into registers while the current one is multiplied out of shared memory.  M, N multiples
+// of 4, K a multiple of 16 (every call site: padded M, 64 * 2^k blocks, 32-wide Cholesky panels).
+// flags (HM_GEMM_*): LOWER  only tiles on or below the block diagonal;  MIRROR  LOWER + the transposed tile is written
+// too (symmetric products);  K_GE / K_LE / KB_GE  restrict the k range of a tile to where triangular operands are non-zero.
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) dgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A,
                                                     int lda, int64_t sA, int64_t subA, const double* __restrict__ B,
                                                     int ldb, int64_t sB, int64_t subB, double beta, double* C, int ldc,
-                                                    int64_t sC, int64_t subC, int nsub, int lower_only) {
-    constexpr int BM = 64, BN = 64, BK = 16;
-    if (lower_only && blockIdx.x > blockIdx.y) return;
+                                                    int64_t sC, int64_t subC, int nsub, int flags) {
+    constexpr int BM = 64, BN = 64, BK = 16, LD = BM + 4;
+    if ((flags & (HM_GEMM_LOWER | HM_GEMM_MIRROR)) && blockIdx.x > blockIdx.y) return;
     {
         const int b = blockIdx.z, q = b / nsub, j = b % nsub;
         A += q * sA + j * subA;
         B += q * sB + j * subB;
         C += q * sC + j * subC;
     }
-    __shared__ double As[BK][BM + 4];
-    __shared__ double Bs[BK][BN + 4];
+    __shared__ __align__(16) double As[BK][LD];
+    __shared__ __align__(16) double Bs[BK][LD];
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     const int row0 = blockIdx.y * BM, col0 = blockIdx.x * BN;
+    int kbeg = 0, kend = K;
+    if (flags & HM_GEMM_K_GE) kbeg = row0 > col0 ? row0 : col0;
+    if (flags & HM_GEMM_KB_GE) kbeg = col0;
+    if (flags & HM_GEMM_K_LE) { const int m = (row0 < col0 ? row0 : col0) + BM; kend = m < K ? m : K; }
+
+    // this thread's share of a k-tile: 4 elements of op(A) and 4 of op(B), contiguous in memory
+    const int ai = TA ? (tid & 15) * 4 : (tid & 63), ak = TA ? (tid >> 4) : (tid >> 6) * 4;
+    const int bj = TB ? (tid & 63) : (tid & 15) * 4, bk = TB ? (tid >> 6) * 4 : (tid >> 4);
+    const bool a_ok = row0 + ai < M, b_ok = col0 + bj < N;
+    const double* ap = TA ? A + (int64_t)ak * lda + row0 + ai : A + (int64_t)(row0 + ai) * lda + ak;
+    const double* bp = TB ? B + (int64_t)(col0 + bj) * ldb + bk : B + (int64_t)bk * ldb + col0 + bj;
+    const int64_t astep = TA ? (int64_t)BK * lda : BK, bstep = TB ? BK : (int64_t)BK * ldb;
+    double2 ra0, ra1, rb0, rb1;
+    auto fetch = [&](int k0) {
+        ra0 = ra1 = rb0 = rb1 = make_double2(0.0, 0.0);
+        if (a_ok) {
+            const double2* p = reinterpret_cast<const double2*>(ap + (int64_t)(k0 / BK) * astep);
+            ra0 = p[0]; ra1 = p[1];
+        }
+        if (b_ok) {
+            const double2* p = reinterpret_cast<const double2*>(bp + (int64_t)(k0 / BK) * bstep);
+            rb0 = p[0]; rb1 = p[1];
+        }
+    };
+    auto stash = [&]() {
+        if (TA) {
+            *reinterpret_cast<double2*>(&As[ak][ai]) = ra0;
+            *reinterpret_cast<double2*>(&As[ak][ai + 2]) = ra1;
+        } else {
+            As[ak][ai] = ra0.x; As[ak + 1][ai] = ra0.y; As[ak + 2][ai] = ra1.x; As[ak + 3][ai] = ra1.y;
+        }
+        if (TB) {
+            Bs[bk][bj] = rb0.x; Bs[bk + 1][bj] = rb0.y; Bs[bk + 2][bj] = rb1.x; Bs[bk + 3][bj] = rb1.y;
+        } else {
+            *reinterpret_cast<double2*>(&Bs[bk][bj]) = rb0;
+            *reinterpret_cast<double2*>(&Bs[bk][bj + 2]) = rb1;
+        }
+    };
     double acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
-    for (int k0 = 0; k0 < K; k0 += BK) {
-#pragma unroll
-        for (int e = tid; e < BM * BK; e += 256) {
-            int i, k;
-            if (!TA) { i = e / BK; k = e % BK; } else { k = e / BM; i = e % BM; }
-            const int gi = row0 + i, gk = k0 + k;
-            double v = 0.0;
-            if (gi < M && gk < K) v = TA ? A[(int64_t)gk * lda + gi] : A[(int64_t)gi * lda + gk];
-            As[k][i] = v;
-        }
-#pragma unroll
-        for (int e = tid; e < BN * BK; e += 256) {
-            int j, k;
-            if (!TB) { k = e / BN; j = e % BN; } else { j = e / BK; k = e % BK; }
-            const int gj = col0 + j, gk = k0 + k;
-            double v = 0.0;
-            if (gj < N && gk < K) v = TB ? B[(int64_t)gj * ldb + gk] : B[(int64_t)gk * ldb + gj];
-            Bs[k][j] = v;
-        }
+    if (kbeg < kend) fetch(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+        stash();
         __syncthreads();
+        if (k0 + BK < kend) fetch(k0 + BK);
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
-            double a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+            const double2 a01 = *reinterpret_cast<const double2*>(&As[kk][ty * 4]);
+            const double2 a23 = *reinterpret_cast<const double2*>(&As[kk][ty * 4 + 2]);
+            const double2 b01 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4]);
+            const double2 b23 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4 + 2]);
+            const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -68,6 +95,7 @@ __global__ void __launch_bounds__(256) dgemm_kernel(int M, int N, int K, double 
         }
         __syncthreads();
     }
+    const bool mirror = (flags & HM_GEMM_MIRROR) && blockIdx.x != blockIdx.y;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int gi = row0 + ty * 4 + i;
@@ -80,18 +108,24 @@ __global__ void __launch_bounds__(256) dgemm_kernel(int M, int N, int K, double 
             double v = alpha * acc[i][j];
             if (beta != 0.0) v += beta * (*c);
             *c = v;
+            if (mirror) C[(int64_t)gj * ldc + gi] = v;
         }
     }
 }
 
 int hm_dgemm(cudaStream_t s, bool ta, bool tb, int M, int N, int K, double alpha, const double* A, int lda, int64_t sA,
              const double* B, int ldb, int64_t sB, double beta, double* C, int ldc, int64_t sC, int batch, int nsub,
-             int64_t subA, int64_t subB, int64_t subC, bool lower_only) {
+             int64_t subA, int64_t subB, int64_t subC, int flags) {
     if (M <= 0 || N <= 0 || batch <= 0) return 0;
+    if ((M | N) % 4 != 0 || K % 16 != 0 || (lda | ldb) % 2 != 0 || ((sA | sB | subA | subB) & 1) ||
+        ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15)) {
+        hm_set_error("hm_dgemm: unsupported shape / alignment (M=%d N=%d K=%d)", M, N, K);
+        return HMOGP_ERR_ARG;
+    }
     dim3 grid((unsigned)hm_cdiv(N, 64), (unsigned)hm_cdiv(M, 64), (unsigned)(batch * nsub));
 #define HM_LAUNCH_GEMM(TA_, TB_)                                                                                      \
     dgemm_kernel<TA_, TB_><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, sA, subA, B, ldb, sB, subB, beta, C, ldc, sC, \
-                                                subC, nsub, lower_only ? 1 : 0)
+                                                subC, nsub, flags)
     if (!ta && !tb) HM_LAUNCH_GEMM(false, false);
     else if (!ta && tb) HM_LAUNCH_GEMM(false, true);
     else if (ta && !tb) HM_LAUNCH_GEMM(true, false);
@@ -110,6 +144,8 @@ __global__ void __launch_bounds__(128) chol_panel_kernel(double* A, int ld, int6
     constexpr int NB = 32;
     A += blockIdx.y * sQ;
     __shared__ double D[NB][NB + 1];
+    __shared__ double invd[NB];   // 1 / D[j][j]: fp64 division and square root are ~350-cycle dependent sequences, and the
+                                  // panel is one long dependent chain of them; one rsqrt per pivot, multiplications elsewhere
     const int tid = threadIdx.x;
     for (int e = tid; e < NB * NB; e += 128) {
         const int i = e / NB, j = e % NB;
@@ -120,9 +156,17 @@ __global__ void __launch_bounds__(128) chol_panel_kernel(double* A, int ld, int6
         const int lane = tid;
         for (int j = 0; j < NB; ++j) {
             double sacc = 0.0;
-            if (lane >= j) {
-                sacc = D[lane][j];
-                for (int l = 0; l < j; ++l) sacc -= D[lane][l] * D[j][l];
+            if (lane >= j) {   // four independent partial sums: the dependent chain is j / 4 FMAs instead of j
+                double s0 = D[lane][j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                int l = 0;
+                for (; l + 4 <= j; l += 4) {
+                    s0 -= D[lane][l] * D[j][l];
+                    s1 -= D[lane][l + 1] * D[j][l + 1];
+                    s2 -= D[lane][l + 2] * D[j][l + 2];
+                    s3 -= D[lane][l + 3] * D[j][l + 3];
+                }
+                for (; l < j; ++l) s0 -= D[lane][l] * D[j][l];
+                sacc = (s0 + s1) + (s2 + s3);
             }
             __syncwarp();
             if (lane == j) {
@@ -130,10 +174,12 @@ __global__ void __launch_bounds__(128) chol_panel_kernel(double* A, int ld, int6
                     if (blockIdx.x == 0) atomicOr(&flags[blockIdx.y], 1);
                     sacc = 1.0;
                 }
-                D[j][j] = sqrt(sacc);
+                const double r = rsqrt(sacc);
+                invd[j] = r;
+                D[j][j] = sacc * r;
             }
             __syncwarp();
-            if (lane > j) D[lane][j] = sacc / D[j][j];
+            if (lane > j) D[lane][j] = sacc * invd[j];
             __syncwarp();
         }
     }
@@ -149,11 +195,14 @@ __global__ void __launch_bounds__(128) chol_panel_kernel(double* A, int ld, int6
 #pragma unroll
         for (int j = 0; j < NB; ++j) x[j] = arow[j];
 #pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            double sacc = x[j];
+        for (int j = 0; j < NB; ++j) {   // four independent partial sums per entry
+            double s0 = x[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-            for (int l = 0; l < j; ++l) sacc -= x[l] * D[j][l];
-            x[j] = sacc / D[j][j];
+            for (int l = 0; l < j; ++l) {
+                const double p = x[l] * D[j][l];
+                if ((l & 3) == 0) s0 -= p; else if ((l & 3) == 1) s1 -= p; else if ((l & 3) == 2) s2 -= p; else s3 -= p;
+            }
+            x[j] = ((s0 + s1) + (s2 + s3)) * invd[j];
         }
 #pragma unroll
         for (int j = 0; j < NB; ++j) arow[j] = x[j];
@@ -171,7 +220,7 @@ int hm_cholesky(cudaStream_t s, double* A, int Mp, int64_t sQ, int Q, int* flags
             const double* P = A + (int64_t)(k0 + NB) * Mp + k0;
             double* C = A + (int64_t)(k0 + NB) * Mp + k0 + NB;
             HM_CHECK(hm_dgemm(s, false, true, rem, rem, NB, -1.0, P, Mp, sQ, P, Mp, sQ, 1.0, C, Mp, sQ, Q, 1, 0, 0, 0,
-                              true));
+                              HM_GEMM_LOWER));
         }
     }
     return 0;
@@ -194,14 +243,24 @@ __global__ void __launch_bounds__(64) triinv_diag_kernel(const double* __restric
     }
     __syncthreads();
     const int c = threadIdx.x;
+    __shared__ double rdiag[NB];   // reciprocal diagonal, computed in parallel: no division in the serial sweep below
+    rdiag[c] = 1.0 / Ls[c][c];
+    __syncthreads();
     for (int i = 0; i < NB; ++i) {
         double v;
         if (i < c) v = 0.0;
-        else if (i == c) v = 1.0 / Ls[c][c];
-        else {
-            double sacc = 0.0;
-            for (int l = c; l < i; ++l) sacc += Ls[i][l] * Xs[l][c];
-            v = -sacc / Ls[i][i];
+        else if (i == c) v = rdiag[c];
+        else {   // four independent partial sums (the chain of dependent shared-memory FMAs dominated this kernel)
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int l = c;
+            for (; l + 4 <= i; l += 4) {
+                s0 += Ls[i][l] * Xs[l][c];
+                s1 += Ls[i][l + 1] * Xs[l + 1][c];
+                s2 += Ls[i][l + 2] * Xs[l + 2][c];
+                s3 += Ls[i][l + 3] * Xs[l + 3][c];
+            }
+            for (; l < i; ++l) s0 += Ls[i][l] * Xs[l][c];
+            v = -((s0 + s1) + (s2 + s3)) * rdiag[i];
         }
         Xs[i][c] = v;
     }

@@ -435,7 +435,7 @@ __global__ void tc_gram_reduce_kernel(const double* __restrict__ slots, const Hm
     const int job = blockIdx.x, q = blockIdx.y;
     const HmGramJob jb = jobs[job];
     const int2 sr = jobslots[q * njobs + job];
-    for (int e = threadIdx.x; e < 128 * jb.nw; e += blockDim.x) {
+    for (int e = blockIdx.z * 8 * jb.nw + threadIdx.x; e < (blockIdx.z + 1) * 8 * jb.nw; e += blockDim.x) {   // 8 rows per CTA
         const int i = e / jb.nw, j = e % jb.nw;
         const int gr = jb.I * 128 + i, gc = jb.j0 + j;
         if (gc > gr || gr >= M) continue;
@@ -444,7 +444,7 @@ __global__ void tc_gram_reduce_kernel(const double* __restrict__ slots, const Hm
         H[((size_t)q * Mp + gr) * Mp + gc] = s;
         if (symmetric) H[((size_t)q * Mp + gc) * Mp + gr] = s;   // plain Grams are symmetric; D^i keeps its lower triangle
     }
-    if (jb.j0 == 0) {
+    if (jb.j0 == 0 && blockIdx.z == 0) {
         for (int e = threadIdx.x; e < nV * 128; e += blockDim.x) {
             const int v = e / 128, i = e % 128;
             if (jb.I * 128 + i >= M) continue;
@@ -499,7 +499,7 @@ int hm_tc_gram(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const HmT
 
 int hm_tc_gram_reduce(cudaStream_t s, const double* slots, const HmGramJob* jobs, const int2* jobslots, int njobs, int Q,
                       const HmGramWeights& gw, double* H, double* g0, int64_t gstride, int M, int Mp) {
-    dim3 grid((unsigned)njobs, (unsigned)Q);
+    dim3 grid((unsigned)njobs, (unsigned)Q, 16u);
     tc_gram_reduce_kernel<<<grid, 256, 0, s>>>(slots, jobs, jobslots, njobs, gw.wdim[0] < 0 ? 1 : 0, gw.nV, H, g0, gstride, M, Mp);
     HM_CUDA(cudaGetLastError());
     return 0;

@@ -489,7 +489,7 @@ __global__ void tc_gram2_reduce_kernel(const double* __restrict__ slots, const H
     const HmGramJob jb = jobs[job];
     const int2 sr = jobslots[q * njobs + job];
     const int row0 = jb.I * 256 + r * 128;
-    for (int e = threadIdx.x; e < 128 * 256; e += blockDim.x) {
+    for (int e = blockIdx.z * 8 * 256 + threadIdx.x; e < (blockIdx.z + 1) * 8 * 256; e += blockDim.x) {   // 8 rows per CTA
         const int i = e >> 8, j = e & 255;
         const int gr = row0 + i, gc = jb.j0 + j;
         if (gc > gr || gr >= M) continue;
@@ -501,7 +501,7 @@ __global__ void tc_gram2_reduce_kernel(const double* __restrict__ slots, const H
         H[((size_t)q * Mp + gr) * Mp + gc] = s;
         H[((size_t)q * Mp + gc) * Mp + gr] = s;
     }
-    if (jb.j0 == 0 && nV > 0) {
+    if (jb.j0 == 0 && nV > 0 && blockIdx.z == 0) {
         for (int i = threadIdx.x; i < 128; i += blockDim.x) {
             if (row0 + i >= M) continue;
             double s = 0.0;
@@ -566,7 +566,7 @@ int hm_tc_gram2(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const Hm
 
 int hm_tc_gram2_reduce(cudaStream_t s, const double* slots, const HmGramJob* jobs, const int2* jobslots, int njobs, int Q, int nV,
                        double* H, double* g0, int M, int Mp) {
-    dim3 grid((unsigned)(2 * njobs), (unsigned)Q);
+    dim3 grid((unsigned)(2 * njobs), (unsigned)Q, 16u);
     tc_gram2_reduce_kernel<<<grid, 256, 0, s>>>(slots, jobs, jobslots, njobs, nV, H, g0, M, Mp);
     HM_CUDA(cudaGetLastError());
     return 0;

@@ -122,7 +122,7 @@ def test_engine_matches_oracle(name, precision):
         # Gamma / Beta rows with posterior variances down to 1e-3 of the prior: v = k_nn + c_n cancels, the split-fp16
         # forward gives v to 1e-2 relative on those rows and dW (a signed sum over rows) to 1e-2; fp32 SIMT: 2e-3.
         # Measured identically with either Gram kernel (HMOGP_TC_GRAM_CTAS=1).
-        tol["grad"] = 2e-2
+        tol["grad"], tol["row"] = 2e-2, 4e-2
     assert err["elbo"] < tol["elbo"]
     for k in GRADS:
         assert err[k] < tol["grad"], (k, err[k])
