@@ -317,22 +317,25 @@ __device__ __forceinline__ void hm_categorical_fast(int K, float y, const float*
             for (int i = 1; i < 10; ++i) { ev = (idx == i) ? e[d][i] : ev; wv = (idx == i) ? w10[i] : wv; }
             eo[d] = ev; base += ev; wo *= wv;
         }
-        float s_in = 0.f, t_in[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) t_in[d] = 0.f;
+        // inner axis D-1.  For the outer axes rho_d = e_d / den with e_d fixed along the inner axis, so
+        //   sum_k w_k rho_d (1 - rho_d) = e_d (I1 - e_d I2),   I1 = sum_k w_k / den_k,  I2 = sum_k w_k / den_k^2
+        float s_in = 0.f, t_last = 0.f, I1 = 0.f, I2 = 0.f;
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
             const float den = base + e[D - 1][k];
             s_in = fmaf(w10[k], hm_lg2(den), s_in);
             if (want_grads) {
-                const float inv = hm_rcp(den);
-#pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    const float rho = ((d == D - 1) ? e[D - 1][k] : eo[d < D - 1 ? d : 0]) * inv;
-                    t_in[d] = fmaf(w10[k], fmaf(-rho, rho, rho), t_in[d]);
-                }
+                const float inv = hm_rcp(den), winv = w10[k] * inv;
+                I1 += winv;
+                I2 = fmaf(winv, inv, I2);
+                const float rho = e[D - 1][k] * inv;
+                t_last = fmaf(w10[k], fmaf(-rho, rho, rho), t_last);
             }
         }
+        float t_in[D];
+#pragma unroll
+        for (int d = 0; d < D - 1; ++d) t_in[d] = eo[d] * fmaf(-eo[d], I2, I1);
+        t_in[D - 1] = t_last;
         S = fmaf(wo, s_in, S);
 #pragma unroll
         for (int d = 0; d < D; ++d) t[d] = fmaf(wo, t_in[d], t[d]);
