@@ -284,7 +284,7 @@ def main():
     issued = {"forward_ms": 3 * 2.0 * work["U"] / (M * M) * Mc * Mc,                       # 3 split-fp16 products, padded M
               "bwd_proj_ms": 3 * 2.0 * work["U"] / (M * M) * Mc * Mc,
               "bwd_gram_ms": 3 * 2.0 * work["U"] / (M * M) * (Mc * Mc) * (0.75 if Mc % 256 == 0 else 0.625)}   # lower block-triangle of 256x256 (pair kernel) / 128x256 tiles
-    traffic = {"bwd_gram_ms": 4.65e8, "forward_ms": 3.08e8, "bwd_proj_ms": 4.97e8}   # dram read+write per launch, ncu --set full (profiles/r1_tc2_ncu_summary.txt)
+    traffic = {"bwd_gram_ms": 3.11e8, "forward_ms": 3.08e8, "bwd_proj_ms": 4.97e8}   # dram read+write per launch, ncu --set full (profiles/r1_tc3_ncu_summary.txt)
     roofline = {"bound": "tensor", "kernel": kern[dom][0], "achieved": ach, "peak": peaks["tc"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tc"],
                 "traffic": traffic.get(dom) if (prec == "tc" and args.config == "cfg3" and world == 1 and not args.rows) else None,
