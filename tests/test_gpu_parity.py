@@ -223,6 +223,30 @@ def test_empty_task_and_row_slices():
     eng.close()
 
 
+def test_host_uploads_pinned_pageable_device_agree():
+    """hmogp_set_data: pageable host memory (copied inside the call), pinned host memory (upload deferred behind the next
+    step's parameter copies, on the copy stream) and device tensors give bit-identical results; a second set_data before
+    the step replaces the first."""
+    import torch
+    prob, g = gu.load_case("cfg2_small")
+    p = pu.params_of(prob)
+    eng = pu.make_engine(prob, "fp64")                                   # pageable numpy
+    ref = eng.evaluate(p, what="full")
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).pin_memory().numpy()
+    junk = [pin(np.zeros_like(x)) for x in prob["X"]]
+    eng.set_data(junk, [pin(y) for y in prob["Y"]])                      # pinned, never used: replaced before the step
+    Xp, Yp = [pin(x) for x in prob["X"]], [pin(y) for y in prob["Y"]]
+    eng.set_data(Xp, Yp)
+    out = eng.evaluate(p, what="full")
+    for k in GRADS + ("log_marginal",):
+        if k in ref:
+            assert np.array_equal(out[k], ref[k]), k
+    eng.set_data([torch.as_tensor(x).cuda() for x in prob["X"]], [torch.as_tensor(y).cuda() for y in prob["Y"]])
+    out = eng.evaluate(p, what="full")
+    assert np.array_equal(out["log_marginal"], ref["log_marginal"])
+    eng.close()
+
+
 def test_shard_sum_equals_whole_large_n():
     """Size-independent property at a large N: the sum of per-shard packed statistics equals the unsharded
     statistics (the all-reduce identity of the multi-GPU path), and ELBO-from-summed-stats equals the whole."""
