@@ -34,7 +34,6 @@ constexpr int kMaxStages = 3;
 // per-CTA stage: NCTA = 1: A (32 KB) + whole B tile (64 KB), 2 stages;  NCTA = 2 (cta_group::2 pair): A + this CTA's
 // half of the B rows (32 KB), 3 stages
 template <int NCTA> struct FwdCfg {
-    static constexpr int stages = (NCTA == 1) ? 2 : 3;
     static constexpr int bhalf = kBHalf / NCTA;
     static constexpr int stage_bytes = 2 * kAHalf + 2 * bhalf;
 };
@@ -124,12 +123,12 @@ __device__ __forceinline__ void two_sum_add(float& hi, float& lo, float x) {
 // (negated so that the packed loops are pure FADD2 / FFMA2:  K = ex2(-(d.d - bias)))
 template <int XD> struct FwdTab { static constexpr int R = 2 * XD + 3; };
 
-template <int XD, int NCTA>
+template <int XD, int NCTA, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const HmTcInfo* __restrict__ info, int64_t ntiles,
               int hyper, int npass) {
     constexpr int R = FwdTab<XD>::R;
-    constexpr int kStages = FwdCfg<NCTA>::stages, kStageBytes = FwdCfg<NCTA>::stage_bytes, kBH = FwdCfg<NCTA>::bhalf;
+    constexpr int kStages = STAGES, kStageBytes = FwdCfg<NCTA>::stage_bytes, kBH = FwdCfg<NCTA>::bhalf;
     constexpr uint32_t kIdesc = idesc_f16(kRows * NCTA, kNB);
     const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;          // 0 = leader of the CTA pair
     const int64_t nsteps = (ntiles + NCTA - 1) / NCTA;                   // row tiles are taken NCTA at a time
@@ -407,20 +406,20 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
     if (warp == kMmaWarp) { if (NCTA == 2) tmem_dealloc2(tmem_base, 512u); else tmem_dealloc(tmem_base, 512u); }
 }
 
-template <int NCTA> size_t fwd_smem_bytes(int Mc, int Xd) {
-    return (size_t)FwdCfg<NCTA>::stages * FwdCfg<NCTA>::stage_bytes + sizeof(float) * ((size_t)Mc * (2 * Xd + 3) + 2 * 4 * 128) +
+template <int NCTA> size_t fwd_smem_bytes(int Mc, int Xd, int stages) {
+    return (size_t)stages * FwdCfg<NCTA>::stage_bytes + sizeof(float) * ((size_t)Mc * (2 * Xd + 3) + 2 * 4 * 128) +
            sizeof(FwdBars) + 64 + 1024;
 }
 
-template <int XD, int NCTA>
-int launch_fwd2(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const void* Cb, const HmTcInfo* info, int64_t ntiles,
+template <int XD, int NCTA, int STAGES>
+int launch_fwd3(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const void* Cb, const HmTcInfo* info, int64_t ntiles,
                 bool hyper, int npass) {
-    const size_t smem = fwd_smem_bytes<NCTA>(a.Mc, XD);
+    const size_t smem = fwd_smem_bytes<NCTA>(a.Mc, XD, STAGES);
     if (smem > 227 * 1024) {
         hm_set_error("tensor-core projection: M=%d (padded %d) with Xdim=%d needs %zu B of shared memory", a.M, a.Mc, XD, smem);
         return HMOGP_ERR_ARG;
     }
-    auto kern = tc_fwd_kernel<XD, NCTA>;
+    auto kern = tc_fwd_kernel<XD, NCTA, STAGES>;
     HM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nw = a.nworkers;
     const int64_t nsteps = (ntiles + NCTA - 1) / NCTA;
@@ -445,8 +444,10 @@ int launch_fwd2(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const vo
 template <int XD>
 int launch_fwd(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const void* Cb, const HmTcInfo* info, int64_t ntiles,
                bool hyper, int npass, int ncta) {
-    if (ncta == 2) return launch_fwd2<XD, 2>(s, tk, a, Cb, info, ntiles, hyper, npass);
-    return launch_fwd2<XD, 1>(s, tk, a, Cb, info, ntiles, hyper, npass);
+    // the per-column tables grow with M: a pair drops from 3 to 2 operand stages when they no longer fit (M > 1536 at Xdim 1)
+    if (ncta == 2 && fwd_smem_bytes<2>(a.Mc, XD, 3) <= 227 * 1024) return launch_fwd3<XD, 2, 3>(s, tk, a, Cb, info, ntiles, hyper, npass);
+    if (ncta == 2) return launch_fwd3<XD, 2, 2>(s, tk, a, Cb, info, ntiles, hyper, npass);
+    return launch_fwd3<XD, 1, 2>(s, tk, a, Cb, info, ntiles, hyper, npass);
 }
 
 }  // namespace
