@@ -393,6 +393,7 @@ struct hmogp_engine {
     double *KLq, *KLpart, *jitter_d, *rowstat, *dzmm;
     cudaStream_t s2;          // side stream of the prepare phase (S, S^-1 branch)
     cudaEvent_t ev_fork, ev_S, ev_Sinv;
+    cudaGraphExec_t chol_graph;   // the 2 Mp / 32 panel + update launches of the blocked Cholesky, captured once
     cudaStream_t sc;          // copy stream: host -> device data uploads overlap the M-sized prepare phase of the next step
     cudaEvent_t ev_cfence, ev_data;
     bool data_pending;        // an upload on sc has not been ordered before the compute stream yet
@@ -470,6 +471,35 @@ HmProjArgs proj_args(hmogp_engine* e) {
 }
 
 int flush_uploads(hmogp_engine* e);
+
+// The blocked Cholesky is 2 Mp / 32 short dependent launches with fixed arguments: replay them as one graph (the gaps
+// between dependent launches are a visible part of the M-sized serial chain).  HMOGP_NO_GRAPH=1 issues them directly.
+int cholesky_graphed(hmogp_engine* e) {
+    static const bool off = [] { const char* v = getenv("HMOGP_NO_GRAPH"); return v && atoi(v) != 0; }();
+    cudaStream_t s = e->stream;
+    if (off) return hm_cholesky(s, e->Luu, e->Mp, (int64_t)e->Mp * e->Mp, e->Q, e->flags_d);
+    if (!e->chol_graph) {
+        cudaStream_t cs;
+        HM_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t g = nullptr;
+        HM_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        const int rc = hm_cholesky(cs, e->Luu, e->Mp, (int64_t)e->Mp * e->Mp, e->Q, e->flags_d);
+        const cudaError_t ce = cudaStreamEndCapture(cs, &g);
+        cudaStreamDestroy(cs);
+        if (rc || ce != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            hm_set_error("Cholesky graph capture failed");
+            return rc ? rc : HMOGP_ERR_CUDA;
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&e->chol_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) { e->chol_graph = nullptr; hm_set_error("Cholesky graph instantiation failed"); return HMOGP_ERR_CUDA; }
+    }
+    HM_CUDA(cudaGraphLaunch(e->chol_graph, s));
+    hm_launch_counter += 2 * (e->Mp / 32) - 1;   // kernels replayed by the graph (panel + trailing update per 32 columns)
+    return 0;
+}
 #ifdef HM_DEBUG_SKIP
 static int dbg_skip() { static int v = -1; if (v < 0) { const char* e = getenv("HMOGP_DEBUG_SKIP"); v = e ? atoi(e) : 0; } return v; }
 #define HM_SKIP(bit) (dbg_skip() & (bit))
@@ -520,7 +550,7 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
         HM_CHECK(hm_build_kuu(s, e->Zp, e->consts, e->jitter_d, e->Kuu, M, Mp, Xd, Q));
         HM_CUDA(cudaMemcpyAsync(e->Luu, e->Kuu, sizeof(double) * sQ * Q, cudaMemcpyDeviceToDevice, s));
         HM_CUDA(cudaMemsetAsync(e->flags_d, 0, sizeof(int) * 2 * HM_MAXQ, s));
-        if (!HM_SKIP(1)) HM_CHECK(hm_cholesky(s, e->Luu, Mp, sQ, Q, e->flags_d));
+        if (!HM_SKIP(1)) HM_CHECK(cholesky_graphed(e));
         int fl[HM_MAXQ];
         HM_CUDA(cudaMemcpyAsync(fl, e->flags_d, sizeof(int) * Q, cudaMemcpyDeviceToHost, s));
         if (!HM_SKIP(64)) HM_CUDA(cudaStreamSynchronize(s));
@@ -876,6 +906,7 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
     }
     e->s2 = nullptr; e->ev_fork = e->ev_S = e->ev_Sinv = nullptr;
     e->sc = nullptr; e->ev_cfence = e->ev_data = nullptr; e->data_pending = false;
+    e->chol_graph = nullptr;
     for (int t = 0; t < HM_MAXT; ++t) e->up_X[t] = e->up_Y[t] = nullptr;
     if (!rc && (cudaStreamCreateWithFlags(&e->s2, cudaStreamNonBlocking) != cudaSuccess ||
                 cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -907,6 +938,7 @@ void hmogp_destroy(hmogp_engine* e) {
     if (e->ev_S) cudaEventDestroy(e->ev_S);
     if (e->ev_Sinv) cudaEventDestroy(e->ev_Sinv);
     if (e->s2) cudaStreamDestroy(e->s2);
+    if (e->chol_graph) cudaGraphExecDestroy(e->chol_graph);
     if (e->ev_cfence) cudaEventDestroy(e->ev_cfence);
     if (e->ev_data) cudaEventDestroy(e->ev_data);
     if (e->sc) cudaStreamDestroy(e->sc);
