@@ -9,15 +9,17 @@
 // Same accumulation scheme as tc_gram.cu (TMEM level 1 -> TMEM level 2 -> fp64 partial tiles), different operand
 // economy.  The weight is split symmetrically: with V[n, m] = 2^kexp K[n,m] sqrt|omega_n| 2^se (K 2^kexp < 2^12, sqrt|omega| 2^se <= 4),
 //     H = 2^-(2 kexp + 2 se) (sgn(omega) V)^T V,
-// so both operands come from ONE generated and split value; the A operand is the B operand with the sign bit of the row
-// flipped (an XOR on the packed fp16 pairs).  A CTA pair owns a 256 x 256 output block: CTA r generates its 128 rows of
+// so both operands come from ONE generated and split value.  When all weights of a 64-row chunk have the same sign (the
+// usual case: omega <= 0 for log-concave likelihoods) the MMA applies the sign through the negate-A bit of its instruction
+// descriptor, and on a diagonal block the A descriptor simply points at the B tile; in a mixed-sign chunk the A operand is
+// the B operand with the sign bit of the row flipped (an XOR on the packed fp16 pairs).  A CTA pair owns a 256 x 256 output block: CTA r generates its 128 rows of
 // A and its 128-column half of B per 64-row chunk (cta_group::2 takes the other half from the peer's shared memory), so
 // a 128 x 256 MMA tile costs 256 generated columns off the diagonal and 128 on it, against 384 in the one-CTA kernel.
 //
 // MMA: D[i (2 x 128 TMEM lanes), j (256 columns)] += A[i][n] . B[j][n]^T over n = 64 data rows per stage (SWIZZLE_128B).
 // Warp roles (640 threads per CTA, one CTA per SM, pairs persistent over a host-built plan of segments):
-//   warps 0-15  generators, two groups of 8 on alternate chunks: (column group of 32) x (32 of the 64 rows); all 16 also
-//               run the level-2/3 flushes
+//   warps 0-15  generators: (column group of 32) x (16 of the 64 rows); all 16 also run the level-2/3 folds (their
+//               16-deep tcgen05.ld parallelism is what keeps a fold at the TMEM read rate)
 //   warp 16     leader: MMA issuer (one thread); peer: relays "my stage is written" to the leader's barrier
 //   warps 17-19 row loaders (x, sqrt|omega|, sign words, mu -> smem ring), alternating groups of 2 chunks
 #include "tc_common.cuh"
@@ -49,7 +51,7 @@ constexpr int kMmaWarp = kGenWarps;
 #ifndef HM_G2_PHASES
 #define HM_G2_PHASES 1
 #endif
-constexpr int kPhases = HM_G2_PHASES;                          // generator warp groups; group p takes the chunks with ring position = p (mod 2)
+constexpr int kPhases = HM_G2_PHASES;               // generator warp groups on alternate chunks (2 was measured slower: the ring is 3 deep)
 constexpr int kPhaseWarps = kGenWarps / kPhases;    // 4 column groups x (4 / kPhases) row parts
 constexpr int kGroups = 2 * kPhases;                // groups of 8 rows per thread and chunk
 constexpr int kLoaders = HM_G2_LOADERS;
