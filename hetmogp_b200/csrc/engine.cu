@@ -395,7 +395,8 @@ struct hmogp_engine {
     cudaEvent_t ev_fork, ev_S, ev_Sinv;
     cudaGraphExec_t chol_graph;   // the 2 Mp / 32 panel + update launches of the blocked Cholesky, captured once
     cudaStream_t sc;          // copy stream: host -> device data uploads overlap the M-sized prepare phase of the next step
-    cudaEvent_t ev_cfence, ev_data;
+    cudaEvent_t ev_cfence, ev_data, ev_dataY;   // inputs X uploaded (the forward needs them) / labels Y too (the likelihoods do)
+    bool dataY_pending;
     bool data_pending;        // an upload on sc has not been ordered before the compute stream yet
     const double* up_X[HM_MAXT];   // deferred uploads from pinned host memory (queued behind the next step's parameter copies,
     const double* up_Y[HM_MAXT];   // so that the M-sized prepare phase is not stuck behind them in the copy engine)
@@ -617,23 +618,32 @@ int flush_uploads(hmogp_engine* e) {
     if (!any) return 0;
     HM_CUDA(cudaEventRecord(e->ev_cfence, e->stream));
     HM_CUDA(cudaStreamWaitEvent(e->sc, e->ev_cfence, 0));
+    // inputs first: the forward pass only needs X, the labels follow while it runs
+    for (int t = 0; t < e->T; ++t)
+        if (e->up_X[t]) HM_CUDA(cudaMemcpyAsync(e->Xd_[t], e->up_X[t], (size_t)e->N[t] * e->Xd * sizeof(double), cudaMemcpyHostToDevice, e->sc));
+    HM_CUDA(cudaEventRecord(e->ev_data, e->sc));
     for (int t = 0; t < e->T; ++t) {
         if (!e->up_X[t]) continue;
-        HM_CUDA(cudaMemcpyAsync(e->Xd_[t], e->up_X[t], (size_t)e->N[t] * e->Xd * sizeof(double), cudaMemcpyHostToDevice, e->sc));
         HM_CUDA(cudaMemcpyAsync(e->Yd_[t], e->up_Y[t], (size_t)e->N[t] * sizeof(double), cudaMemcpyHostToDevice, e->sc));
         e->up_X[t] = e->up_Y[t] = nullptr;
     }
-    HM_CUDA(cudaEventRecord(e->ev_data, e->sc));
+    HM_CUDA(cudaEventRecord(e->ev_dataY, e->sc));
+    e->dataY_pending = true;
     e->data_pending = true;
     return 0;
 }
 
-// order pending row uploads (copy stream) before whatever is queued next on the compute stream
-int data_ready(hmogp_engine* e) {
+// order pending row uploads (copy stream) before whatever is queued next on the compute stream: the inputs X, and with
+// labels = true also Y
+int data_ready(hmogp_engine* e, bool labels = true) {
     HM_CHECK(flush_uploads(e));
     if (e->data_pending) {
         HM_CUDA(cudaStreamWaitEvent(e->stream, e->ev_data, 0));
         e->data_pending = false;
+    }
+    if (labels && e->dataY_pending) {
+        HM_CUDA(cudaStreamWaitEvent(e->stream, e->ev_dataY, 0));
+        e->dataY_pending = false;
     }
     return 0;
 }
@@ -905,7 +915,7 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
             if (cudaEventCreate(&e->ev[i]) != cudaSuccess) { hm_set_error("cudaEventCreate failed"); rc = HMOGP_ERR_CUDA; break; }
     }
     e->s2 = nullptr; e->ev_fork = e->ev_S = e->ev_Sinv = nullptr;
-    e->sc = nullptr; e->ev_cfence = e->ev_data = nullptr; e->data_pending = false;
+    e->sc = nullptr; e->ev_cfence = e->ev_data = e->ev_dataY = nullptr; e->data_pending = e->dataY_pending = false;
     e->chol_graph = nullptr;
     for (int t = 0; t < HM_MAXT; ++t) e->up_X[t] = e->up_Y[t] = nullptr;
     if (!rc && (cudaStreamCreateWithFlags(&e->s2, cudaStreamNonBlocking) != cudaSuccess ||
@@ -914,7 +924,8 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
                 cudaEventCreateWithFlags(&e->ev_Sinv, cudaEventDisableTiming) != cudaSuccess ||
                 cudaStreamCreateWithFlags(&e->sc, cudaStreamNonBlocking) != cudaSuccess ||
                 cudaEventCreateWithFlags(&e->ev_cfence, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&e->ev_data, cudaEventDisableTiming) != cudaSuccess)) {
+                cudaEventCreateWithFlags(&e->ev_data, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&e->ev_dataY, cudaEventDisableTiming) != cudaSuccess)) {
         hm_set_error("side stream / event creation failed");
         rc = HMOGP_ERR_CUDA;
     }
@@ -941,6 +952,7 @@ void hmogp_destroy(hmogp_engine* e) {
     if (e->chol_graph) cudaGraphExecDestroy(e->chol_graph);
     if (e->ev_cfence) cudaEventDestroy(e->ev_cfence);
     if (e->ev_data) cudaEventDestroy(e->ev_data);
+    if (e->ev_dataY) cudaEventDestroy(e->ev_dataY);
     if (e->sc) cudaStreamDestroy(e->sc);
     delete e;
 }
@@ -1022,7 +1034,7 @@ int hmogp_step_local(hmogp_engine* e, const hmogp_params* p, int32_t mem_kind, i
     e->launch0 = hm_launch_counter;
     if (e->timing) HM_CUDA(cudaEventRecord(e->ev[0], s));
     HM_CHECK(mm_prepare(e, p, mem_kind));
-    HM_CHECK(data_ready(e));
+    HM_CHECK(data_ready(e, false));   // X only; the labels are awaited before the likelihood kernels
     if (e->timing) HM_CUDA(cudaEventRecord(e->ev[1], s));
     HM_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (what >= HMOGP_WHAT_VE ? (int64_t)e->off_H : e->stats_len), s));
     HmProjArgs pa = proj_args(e);
@@ -1034,6 +1046,7 @@ int hmogp_step_local(hmogp_engine* e, const hmogp_params* p, int32_t mem_kind, i
     } else HM_CHECK(hm_proj_fwd(s, e->prec, e->tk, pa));
     if (e->timing) HM_CUDA(cudaEventRecord(e->ev[2], s));
     // ---- likelihoods
+    HM_CHECK(data_ready(e, true));
     const int simt_prec = (e->prec == HMOGP_PREC_FP64) ? HMOGP_PREC_FP64 : HMOGP_PREC_FP32;
     for (int t = 0; t < e->T; ++t) {
         int nb = 0;

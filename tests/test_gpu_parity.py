@@ -236,7 +236,7 @@ def test_host_uploads_pinned_pageable_device_agree():
     prob, g = gu.load_case("cfg2_small")
     p = pu.params_of(prob)
     eng = pu.make_engine(prob, "fp64")                                   # pageable numpy
-    ref = eng.evaluate(p, what="full")
+    ref = {k: np.array(v) for k, v in eng.evaluate(p, what="full").items()}   # host results are views of engine buffers
     pin = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).pin_memory().numpy()
     junk = [pin(np.zeros_like(x)) for x in prob["X"]]
     eng.set_data(junk, [pin(y) for y in prob["Y"]])                      # pinned, never used: replaced before the step
@@ -248,7 +248,14 @@ def test_host_uploads_pinned_pageable_device_agree():
             assert np.array_equal(out[k], ref[k]), k
     eng.set_data([torch.as_tensor(x).cuda() for x in prob["X"]], [torch.as_tensor(y).cuda() for y in prob["Y"]])
     out = eng.evaluate(p, what="full")
-    assert np.array_equal(out["log_marginal"], ref["log_marginal"])
+    assert np.array_equal(out["log_marginal"], ref["log_marginal"]) and np.array_equal(out["dZ"], ref["dZ"])
+    # host outputs alternate between two page-locked buffer sets: a result stays valid across exactly one further call
+    first = eng.evaluate(pu.params_of(prob), what="full")
+    keep = first["dZ"].copy()
+    p2 = dict(pu.params_of(prob))
+    p2["m_u"] = p2["m_u"] * 1.5
+    second = eng.evaluate(p2, what="full")
+    assert np.array_equal(first["dZ"], keep) and not np.array_equal(second["dZ"], keep)
     eng.close()
 
 
