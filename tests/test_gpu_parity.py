@@ -136,6 +136,20 @@ def test_engine_matches_oracle(name, precision):
             assert v < tol["row"], (k, v)
 
 
+def test_single_cta_kernel_variants(monkeypatch):
+    """The one-CTA forward (HMOGP_TC_FWD_CTAS=1) and the one-CTA Gram kernel (HMOGP_TC_GRAM_CTAS=1, tc_gram.cu) stay
+    selectable and correct: same oracle case as the default CTA-pair kernels."""
+    monkeypatch.setenv("HMOGP_TC_FWD_CTAS", "1")
+    monkeypatch.setenv("HMOGP_TC_GRAM_CTAS", "1")
+    c = dict(CASES["pad_m300"])
+    prob = synth.make_problem(c.pop("liks"), c.pop("N"), c.pop("M"), c.pop("Q"), Xdim=c.pop("Xdim"), seed=7, **c)
+    err, out, o = pu.compare(prob, "tc")
+    tol = TOL["tc"]
+    assert err["elbo"] < tol["elbo"]
+    for k in GRADS:
+        assert err[k] < tol["grad"], (k, err[k])
+
+
 def test_what_levels_and_stale_chain():
     """ELBO-only / VE-step / full agree on shared outputs; W_chain (quirk C-5) follows the oracle."""
     prob, g = gu.load_case("cfg3_small")
