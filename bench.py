@@ -8,23 +8,23 @@
 
 Workload (config.workload): BASELINE.json configs[2] "cfg3" -- N=1e6 rows per output, M=500, Q=3 RBF latents,
 T=5 outputs [HetGaussian, Bernoulli, Categorical(K=4), Gamma, Beta] (J=10 output functions), seeded synthetic data.
-One step = one evaluation equivalent to SVMOGP.parameters_changed(): ELBO and ALL gradients (q(U), Z, kernel and
-coregionalisation hyper-parameters).  Total N is fixed; under torchrun the rows are sharded over the ranks and the
-packed sufficient statistics are summed with one NCCL all-reduce per step ("strong" scaling).
+One step = one evaluation equivalent to SVMOGP.parameters_changed() -- ELBO and ALL gradients (q(U), Z,
+kernel and coregionalisation hyper-parameters) -- plus one optimiser update of the flat parameter vector (climin
+Adadelta, util.py:327: look-ahead + update kernels of csrc/optim.cu, on the device).  Total N is fixed; under torchrun
+the rows are sharded over the ranks and the packed sufficient statistics are summed with one NCCL all-reduce per step
+("strong" scaling).
 
-value   steps/s with X, Y and the parameters resident in HBM (device pointers through the C-ABI).
+value   steps/s with X, Y, the parameters, the gradients and the optimiser state resident in HBM.
 e2e     steps/s through the reference-facing call SVMOGPInf.inference(...) with HOST numpy buffers (pinned): every
-        step uploads X, Y and the parameters and downloads ELBO + gradients inside the timed region.
+        step uploads X, Y and the parameters, downloads ELBO + gradients and applies the Adadelta update to the host
+        vector, all inside the timed region.  e2e_pageable: the same with ordinary (pageable) numpy arrays.
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
-
-import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -40,10 +40,33 @@ def parse():
     ap.add_argument("--rows", type=int, default=None, help="rows per task (default: the config's N)")
     ap.add_argument("--precision", default=os.environ.get("HMOGP_PRECISION", "auto"))
     ap.add_argument("--what", default="full", choices=["full", "ve", "elbo"])
-    ap.add_argument("--cpu-rows", type=int, default=5000, help="rows per task of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-rows", type=int, default=20000, help="rows per task of the bounded CPU-baseline sample (2 %% of cfg3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-size comparison against the fp64 mode")
+    ap.add_argument("--no-variants", action="store_true", help="skip the VE-step / ELBO-only side measurements")
+    ap.add_argument("--no-optimizer", action="store_true", help="time the evaluation alone (no Adadelta update)")
     return ap.parse_args()
+
+
+ARGS = parse()
+if ARGS.impl == "reference":
+    # The CPU arm uses every host core (torchrun exports OMP_NUM_THREADS=1: override it) -- before numpy loads its BLAS.
+    _n = str(os.cpu_count() or 1)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[_k] = _n
+
+import numpy as np  # noqa: E402
+
+
+def load_synth():
+    """The input generator (pure numpy) loaded by file path: importing the hetmogp_b200 package would map the CUDA
+    library, which the CPU arm must never do."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("hmogp_bench_synth", os.path.join(ROOT, "hetmogp_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def load_peaks():
@@ -62,6 +85,7 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
 
     def run(self):
+        import subprocess
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self._stop_evt.is_set():
@@ -79,10 +103,11 @@ class ClockSampler(threading.Thread):
         self.join(timeout=6)
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "power_w_median": float(np.median(pw)) if pw else None, "samples": len(self.rows)}
 
 
 def algorithmic_work(N_tasks, M, Q, Xdim, what="full"):
@@ -97,60 +122,101 @@ def algorithmic_work(N_tasks, M, Q, Xdim, what="full"):
                 bytes=float(sum(N_tasks)) * (Xdim + 1) * 8)
 
 
-def cpu_baseline(cfg_name, n_rows, steps=1):
-    """The CPU path beside the GPU number: diag-only fp64 numpy/OpenBLAS port of the reference's algorithm
-    (oracle/diag_oracle.py; arithmetic-identical to hetmogp/svmogp_inf.py for ELBO and gradients) on
-    a bounded row sample of the same workload; cost is linear in N, so steps/s is extrapolated to the full N."""
-    from hetmogp_b200 import synth
+# --------------------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(synth, cfg_name, n_rows, reps):
+    """The diag-only fp64 numpy/OpenBLAS port of the reference's algorithm (oracle/diag_oracle.py; arithmetic-identical to
+    hetmogp/svmogp_inf.py for ELBO and gradients) on a bounded row sample of the workload, `reps` times."""
     from oracle import diag_oracle
-    c = synth.CONFIGS[cfg_name]
     prob = synth.make_config(cfg_name, N=n_rows)
     ts = []
-    for _ in range(max(1, steps)):
+    for _ in range(max(1, reps)):
         t0 = time.perf_counter()
         diag_oracle.elbo_and_grads(prob, chunk=8192)
         ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def cpu_baseline(synth, cfg_name, n_rows, reps=1):
+    c = synth.CONFIGS[cfg_name]
+    ts = cpu_sample(synth, cfg_name, n_rows, reps)
     t = float(np.median(ts))
-    full_t = t * (c["N"] / float(n_rows))
+    full_t = t * (c["N"] / float(n_rows))               # the cost is linear in N
     return {"value": 1.0 / full_t, "unit": "ELBO steps/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": "%d of %d rows per task (all %d tasks), %.2f s per sample step, extrapolated linearly in N" % (n_rows, c["N"], len(c["liks"]), t),
-            "sample_seconds": t}
+            "threads_env": os.environ.get("OMP_NUM_THREADS"),
+            "sample": "%d of %d rows per task (%.1f %%, all %d tasks), median of %d: %.2f s per sample step, extrapolated linearly in N"
+                      % (n_rows, c["N"], 100.0 * n_rows / c["N"], len(c["liks"]), len(ts), t),
+            "sample_seconds": t, "sample_seconds_all": ts}
+
+
+def reference_extras(synth):
+    """the literal reference (verbatim SVMOGPInf.inference, O(N^2)) at cfg1 where the reference tree
+    exists -- the port at cfg1 otherwise -- and one true full-N run of the port at cfg2."""
+    extra = {}
+    from oracle import diag_oracle
+    try:
+        from oracle import verbatim
+        p1 = synth.make_config("cfg1")
+        if verbatim.available():
+            verbatim.run_inference(p1)
+            t0 = time.perf_counter()
+            verbatim.run_inference(p1)
+            extra["cfg1_verbatim_reference_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        diag_oracle.elbo_and_grads(p1)
+        extra["cfg1_port_s"] = time.perf_counter() - t0
+        p2 = synth.make_config("cfg2")
+        t0 = time.perf_counter()
+        diag_oracle.elbo_and_grads(p2, chunk=8192)
+        extra["cfg2_port_full_N_s"] = time.perf_counter() - t0
+    except Exception as e:  # never lose the headline line to a side measurement
+        extra["error"] = repr(e)
+    return extra
 
 
 def run_reference(args, rank, world):
+    """CPU arm.  Every step is one bounded sample of the workload: the first three timed steps take the full 2 % sample
+    (args.cpu_rows rows per task), further steps a quarter of it, so that --steps 20 --warmup 5 still ends in a few
+    minutes; the cost is linear in N, each sample is scaled to the full N and the reported value is the median over the
+    2 % samples (the smaller ones are listed for consistency)."""
     if rank != 0:
         return
-    c_rows = args.cpu_rows
-    base = None
-    ts = []
-    for i in range(args.warmup + args.steps):
-        b = cpu_baseline(args.config, c_rows, steps=1)
-        if i >= args.warmup:
-            ts.append(b["sample_seconds"])
-        base = b
-    from hetmogp_b200 import synth
+    synth = load_synth()
     c = synth.CONFIGS[args.config]
-    t = float(np.mean(ts)) * (c["N"] / float(c_rows))
-    base["value"] = 1.0 / t
-    base["sample_seconds"] = float(np.mean(ts))
+    big, small = args.cpu_rows, max(1000, args.cpu_rows // 4)
+    for _ in range(args.warmup):
+        cpu_sample(synth, args.config, max(500, small // 4), 1)                 # warm the BLAS threads / caches, untimed
+    sizes = [big] * min(3, args.steps) + [small] * max(0, args.steps - 3)
+    full = []
+    for n in sizes:
+        full.append(cpu_sample(synth, args.config, n, 1)[0] * (c["N"] / float(n)))
+    t = float(np.median(full[:min(3, args.steps)]))
+    base = {"value": 1.0 / t, "unit": "ELBO steps/s", "cores": os.cpu_count(), "kind": "port",
+            "threads_env": os.environ.get("OMP_NUM_THREADS"),
+            "sample": "%d of %d rows per task (%.1f %%, all %d tasks) in the first %d timed steps (median: %.2f s per sample), %d rows in the "
+                      "other %d; every sample scaled linearly to the full N" % (big, c["N"], 100.0 * big / c["N"], len(c["liks"]),
+                                                                                min(3, args.steps), t * big / c["N"], small, max(0, args.steps - 3)),
+            "full_N_seconds_per_sample": full, "extras": reference_extras(synth)}
     line = {"impl": "reference", "metric": "ELBO steps/sec (ELBO + all gradients)", "value": 1.0 / t, "unit": "ELBO steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, c), "cpu_baseline": base,
+            "native_library_loaded": any("hetmogp_b200" in m for m in sys.modules),
             "e2e": {"value": 1.0 / t, "unit": "ELBO steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def workload_config(args, c):
     N = args.rows or c["N"]
-    return {"workload": "%s: N=%d rows/output, M=%d, Q=%d, T=%d outputs %s, Xdim=%d; step = ELBO + all gradients (%s)" % (
-        args.config, N, c["M"], c["Q"], len(c["liks"]), [s[0] + (str(s[1]) if s[0] == "Categorical" else "") for s in c["liks"]], c["Xdim"], args.what),
+    return {"workload": "%s: N=%d rows/output, M=%d, Q=%d, T=%d outputs %s, Xdim=%d; step = ELBO + all gradients (%s)%s" % (
+        args.config, N, c["M"], c["Q"], len(c["liks"]), [s[0] + (str(s[1]) if s[0] == "Categorical" else "") for s in c["liks"]], c["Xdim"], args.what,
+        "" if (args.no_optimizer or args.impl == "reference") else " + one Adadelta update of the flat parameter vector"),
         "l2": "working set per step (X, Y, per-row a/c and row weights, Gram partials: >0.5 GB) exceeds the 126 MB L2; "
               "a 256 MB buffer is also written between timed iterations", "seed": 1234 + int(args.config[3:])}
 
 
+# --------------------------------------------------------------------------------------------------- our arm
 def main():
-    args = parse()
+    args = ARGS
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -158,6 +224,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    import ctypes as C
     import torch
     import torch.distributed as dist
     from hetmogp_b200 import Engine, shard_rows, synth, _lib
@@ -165,6 +232,8 @@ def main():
     from hetmogp_b200 import likelihoods as L
     from hetmogp_b200.het_likelihood import HetLikelihood
     from hetmogp_b200.gpy_shim import RBF, Coregionalize
+    from hetmogp_b200.optim import Adadelta
+    lib, check = _lib.lib, _lib.check
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -175,35 +244,67 @@ def main():
         group = dist.group.WORLD
     prec = args.precision
     if prec == "auto":
-        prec = "tc" if _lib.lib.hmogp_tc_built() else "fp32"
+        prec = "tc" if lib.hmogp_tc_built() else "fp32"
 
     c = synth.CONFIGS[args.config]
     N = args.rows or c["N"]
     prob = synth.make_config(args.config, N=N)            # same seed on every rank -> same data, each keeps its shard
-    T, Q, M, Xdim = prob["T"], prob["Q"], prob["M"], prob["Xdim"]
+    T, Q, M, Xdim, J = prob["T"], prob["Q"], prob["M"], prob["Xdim"], prob["J"]
     Ns = [x.shape[0] for x in prob["X"]]
     begin, count = shard_rows(Ns, rank, world)
     Xs = [prob["X"][t][begin[t]:begin[t] + count[t]] for t in range(T)]
     Ys = [prob["Y"][t][begin[t]:begin[t] + count[t]] for t in range(T)]
     bscale = [1.0] * T
+    what_id = {"elbo": 0, "ve": 1, "full": 2}[args.what]
 
     # ---------------------------------------------------------------- resident arm ("value")
     eng = Engine(prob["lik_specs"], M, Q, Xdim, precision=prec, device=local, group=group)
-    eng.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    eng.set_stream(stream)
     eng.set_data([torch.as_tensor(x, device=dev) for x in Xs], [torch.as_tensor(y, device=dev) for y in Ys])
     pkeys = ("Z", "m_u", "L_u", "rbf_var", "rbf_ls", "W", "kappa")
     params_dev = {k: torch.as_tensor(np.ascontiguousarray(prob[k]), device=dev) for k in pkeys}
     params_dev["batch_scale"] = torch.as_tensor(np.asarray(bscale), device=dev)
-    out_dev, _ = eng._alloc_out({"elbo": 0, "ve": 1, "full": 2}[args.what], True, False)
+    out_dev, _ = eng._alloc_out(what_id, True, False)
+    for v in out_dev.values():
+        v.zero_()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     eng.enable_timing(True)
+
+    # Optimiser over paramz' flat vector (svmogp.py:71-75 link order; kappa fixed as util.py:289 does, the lengthscale
+    # free as in the VM steps of util.py:307): Adadelta state and both kernels on the device.
+    opt = None
+    n_opt = 0
+    if not args.no_optimizer and what_id >= 1:
+        segs = [(params_dev["m_u"], out_dev["dL_dmu_u"], M * Q, 1, 0, 1, 0, 0), (params_dev["L_u"], out_dev["dL_dL_u"], prob["L_u"].size, 1, 0, 1, 0, 0)]
+        if what_id == 2:
+            segs = [(params_dev["Z"], out_dev["dZ"], M * Q * Xdim, 1, 0, 0, 0, 0)] + segs
+            for q in range(Q):
+                segs += [(params_dev["rbf_var"], out_dev["d_rbf"], 1, 1, 1, 0, q, 2 * q), (params_dev["rbf_ls"], out_dev["d_rbf"], 1, 1, 1, 0, q, 2 * q + 1)]
+            for q in range(Q):
+                segs += [(params_dev["W"], out_dev["dW"], J, Q, 0, 0, q, q)]
+        arr = (_lib.OptSegment * len(segs))()
+        for i, (pt, gt, n, stride, pos, var, po, go) in enumerate(segs):
+            arr[i].offset, arr[i].count, arr[i].param, arr[i].grad = n_opt, n, pt.data_ptr() + 8 * po, gt.data_ptr() + 8 * go
+            arr[i].stride, arr[i].positive, arr[i].variational, arr[i].reserved = stride, pos, var, 0
+            n_opt += n
+        opt = C.c_void_p()
+        check(lib.hmogp_opt_create(local, arr, len(segs), 0.01, 0.9, 0.9, 1e-4, C.byref(opt)))
+        check(lib.hmogp_opt_gather(opt, C.c_void_p(stream)))
+
+    def resident_step():
+        if opt is not None:
+            check(lib.hmogp_opt_lookahead(opt, 1, C.c_void_p(stream)))
+        eng.evaluate(params_dev, what=args.what, out=out_dev)
+        if opt is not None:
+            check(lib.hmogp_opt_update(opt, 1, 1, None, C.c_void_p(stream)))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps, warmup, sampler=None):
+    def timed(fn, steps, warmup, sampler=None, engine=None):
         for _ in range(warmup):
             fn()
         barrier()
@@ -220,7 +321,8 @@ def main():
             b.record()
             b.synchronize()
             per.append(a.elapsed_time(b))
-            phase.append(eng.last_timing())
+            if engine is not None:
+                phase.append(engine.last_timing())
         barrier()
         wall = time.perf_counter() - t_wall
         tot = torch.tensor([sum(per)], dtype=torch.float64, device=dev)
@@ -229,33 +331,85 @@ def main():
         return float(tot.item()) / steps, phase, wall
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_step, phases, wall = timed(lambda: eng.evaluate(params_dev, what=args.what, out=out_dev), args.steps, max(3, args.warmup), sampler)
+    ms_step, phases, wall = timed(resident_step, args.steps, max(3, args.warmup), sampler, eng)
     clocks = sampler.stop() if sampler else None
     elbo_resident = float(out_dev["log_marginal"].cpu()[0, 0])
-    launches = int(np.sum([p["launches"] for p in phases]))
+    launches = int(np.sum([p["launches"] for p in phases])) + (2 * args.steps if opt is not None else 0)
+
+    # side measurements on the same resident data: evaluation only, VE step, ELBO only (SURVEY 8d asks for them)
+    variants = None
+    if not args.no_variants and args.what == "full":
+        variants = {}
+        p0 = {k: torch.as_tensor(np.ascontiguousarray(prob[k]), device=dev) for k in pkeys}
+        p0["batch_scale"] = params_dev["batch_scale"]
+        for name, w in (("evaluation_only", "full"), ("ve_step", "ve"), ("elbo_only", "elbo")):
+            o, _ = eng._alloc_out({"elbo": 0, "ve": 1, "full": 2}[w], True, False)
+            ms, _, _ = timed(lambda: eng.evaluate(p0, what=w, out=o), max(3, args.steps), 2)
+            variants[name] = {"ms_per_step": ms, "steps_per_s": 1e3 / ms}
 
     # ---------------------------------------------------------------- end-to-end arm (host buffers through the plugin API)
     e2e = None
+    e2e_pageable = None
     if not args.no_e2e:
-        pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory().numpy()
-        Xh, Yh = [pin(x) for x in Xs], [pin(y) for y in Ys]
         liks = HetLikelihood([L.from_spec(s) for s in prob["lik_specs"]])
         meta = liks.generate_metadata()
-        kern_list = [RBF(Xdim, variance=prob["rbf_var"][q], lengthscale=prob["rbf_ls"][q]) for q in range(Q)]
-        B_list = [Coregionalize(Xdim, prob["J"], 1, W=prob["W"][:, q:q + 1], kappa=prob["kappa"][:, q]) for q in range(Q)]
-        m_u, L_u, Z = pin(prob["m_u"]), pin(prob["L_u"]), pin(prob["Z"])
-        inf = SVMOGPInf(precision=prec, device=local, group=group)
-        inf._eng, inf._key = eng, (tuple(tuple(l.spec) for l in liks.likelihoods_list), M, Q, Xdim, prec, local)
-        res = {}
+        h2d = sum(x.nbytes + y.nbytes for x, y in zip(Xs, Ys)) + sum(np.asarray(prob[k]).nbytes for k in pkeys) + 8 * T
+        d2h = 8 * (2 + T + M * Q + (M * (M + 1) // 2) * Q + Q * M * M + 2 * Q + 2 * J * Q + M * Q * Xdim)
 
-        def e2e_step():
-            lm, grads, _, _ = inf.inference(m_u, L_u, Xh, Yh, Z, kern_list, liks, B_list, meta, batch_scale=bscale, what=args.what)
-            res["lm"] = float(lm[0, 0])
-        ms_e2e, _, _ = timed(e2e_step, args.steps, 3)
-        h2d = sum(x.nbytes + y.nbytes for x, y in zip(Xh, Yh)) + sum(np.asarray(prob[k]).nbytes for k in pkeys) + 8 * T
-        d2h = 8 * (2 + T + M * Q + (M * (M + 1) // 2) * Q + Q * M * M + 2 * Q + 2 * prob["J"] * Q + M * Q * Xdim)
-        e2e = {"value": 1e3 / ms_e2e, "unit": "ELBO steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": ms_e2e, "elbo": res.get("lm")}
+        def e2e_arm(pinned):
+            pin = (lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory().numpy()) if pinned else (lambda a: np.array(a, order="C"))
+            Xh, Yh = [pin(x) for x in Xs], [pin(y) for y in Ys]
+            kern_list = [RBF(Xdim, variance=prob["rbf_var"][q], lengthscale=prob["rbf_ls"][q]) for q in range(Q)]
+            B_list = [Coregionalize(Xdim, J, 1, W=prob["W"][:, q:q + 1], kappa=prob["kappa"][:, q]) for q in range(Q)]
+            m_u, L_u, Z = pin(prob["m_u"]), pin(prob["L_u"]), pin(prob["Z"])
+            inf = SVMOGPInf(precision=prec, device=local, group=group)
+            inf._eng, inf._key = eng, (tuple(tuple(l.spec) for l in liks.likelihoods_list), M, Q, Xdim, prec, local)
+            res = {}
+            nq = m_u.size + L_u.size
+
+            def fprime(w):       # the reference's stochastic_grad shape: parameters in, -gradient out, through inference()
+                m_u[...] = w[:m_u.size].reshape(m_u.shape)
+                L_u[...] = w[m_u.size:nq].reshape(L_u.shape)
+                lm, grads, _, _ = inf.inference(m_u, L_u, Xh, Yh, Z, kern_list, liks, B_list, meta, batch_scale=bscale, what=args.what)
+                res["lm"] = float(lm[0, 0])
+                if "dL_dmu_u" not in grads:
+                    return np.zeros_like(w)
+                return -np.concatenate([np.hstack(grads["dL_dmu_u"]).ravel(), np.hstack(grads["dL_dL_u"]).ravel()])
+            it = iter(Adadelta(np.concatenate([m_u.ravel(), L_u.ravel()]), fprime, step_rate=0.01, momentum=0.9))
+            ms, _, _ = timed(lambda: next(it), args.steps, 3)
+            return {"value": 1e3 / ms, "unit": "ELBO steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms, "elbo": res.get("lm"), "host_buffers": "pinned" if pinned else "pageable",
+                    "optimizer": "Adadelta update of q(U) on the host vector inside the timed region"}
+        e2e = e2e_arm(True)
+        e2e_pageable = e2e_arm(False)
+
+    # ---------------------------------------------------------------- full-size parity: tc (or fp32) against the fp64 mode
+    parity = None
+    if not args.no_parity and world == 1 and prec != "fp64" and args.what == "full":
+        try:
+            p0 = {k: torch.as_tensor(np.ascontiguousarray(prob[k]), device=dev) for k in pkeys}
+            p0["batch_scale"] = params_dev["batch_scale"]
+            o_t, _ = eng._alloc_out(2, True, True)
+            eng.evaluate(p0, what="full", want_dKmm=True, out=o_t)
+            ref = Engine(prob["lik_specs"], M, Q, Xdim, precision="fp64", device=local)
+            ref.set_data([torch.as_tensor(x, device=dev) for x in Xs], [torch.as_tensor(y, device=dev) for y in Ys])
+            o_r, _ = ref._alloc_out(2, True, True)
+            t0 = time.perf_counter()
+            ref.evaluate(p0, what="full", want_dKmm=True, out=o_r)
+            torch.cuda.synchronize(dev)
+            t_ref = time.perf_counter() - t0
+            ref.close()
+
+            def rel(k):
+                a, b = o_t[k], o_r[k]
+                return float((a - b).abs().max() / b.abs().max())
+            parity = {"against": "fp64 mode of the same engine (itself held to 1e-7 of the CPU oracle by the GPU tests), same N",
+                      "norm": "max|a-b| / max|b| per block", "fp64_mode_seconds": t_ref,
+                      "elbo": abs(float(o_t["log_marginal"][0, 0] - o_r["log_marginal"][0, 0])) / abs(float(o_r["log_marginal"][0, 0]))}
+            for k in ("dL_dmu_u", "dL_dL_u", "dL_dKmm", "d_rbf", "dW", "dkappa", "dZ"):
+                parity[k] = rel(k)
+        except Exception as e:
+            parity = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -280,37 +434,50 @@ def main():
     dom = max(kern, key=lambda k: per_launch[k])
     ach = kern[dom][1] / (per_launch[dom] * 1e-3) / 1e12 if per_launch[dom] > 0 else 0.0
     n_kernel_ms = sum(med.get(k, 0.0) for k in kern)
-    Mc = -(-M // 256) * 256
-    issued = {"forward_ms": 3 * 2.0 * work["U"] / (M * M) * Mc * Mc,                       # 3 split-fp16 products, padded M
-              "bwd_proj_ms": 3 * 2.0 * work["U"] / (M * M) * Mc * Mc,
-              "bwd_gram_ms": 3 * 2.0 * work["U"] / (M * M) * (Mc * Mc) * (0.75 if Mc % 256 == 0 else 0.625)}   # lower block-triangle of 256x256 (pair kernel) / 128x256 tiles
-    traffic = {"bwd_gram_ms": 3.11e8, "forward_ms": 3.08e8, "bwd_proj_ms": 4.97e8}   # dram read+write per launch, ncu --set full (profiles/r1_tc3_ncu_summary.txt)
+    tinfo = eng.tc_info() if (prec == "tc" and hasattr(eng, "tc_info")) else {}
+    Mc = tinfo.get("Mc", -(-M // 256) * 256)
+    passes = tinfo.get("passes", {"forward_ms": 3, "bwd_proj_ms": 3, "bwd_gram_ms": 3})
+    gram_frac = tinfo.get("gram_block_fraction", 0.75 if Mc % 256 == 0 else 0.625)
+    issued = {"forward_ms": passes["forward_ms"] * 2.0 * work["U"] / (M * M) * Mc * Mc,           # MMA products issued, padded M
+              "bwd_proj_ms": passes["bwd_proj_ms"] * 2.0 * work["U"] / (M * M) * Mc * Mc,
+              "bwd_gram_ms": passes["bwd_gram_ms"] * 2.0 * work["U"] / (M * M) * (Mc * Mc) * gram_frac}
+    traffic_ncu = {"bwd_gram_ms": 3.11e8, "forward_ms": 3.08e8, "bwd_proj_ms": 4.97e8}
+    headline = prec == "tc" and args.config == "cfg3" and world == 1 and not args.rows
     roofline = {"bound": "tensor", "kernel": kern[dom][0], "achieved": ach, "peak": peaks["tc"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tc"],
-                "traffic": traffic.get(dom) if (prec == "tc" and args.config == "cfg3" and world == 1 and not args.rows) else None,
+                "traffic": traffic_ncu.get(dom) if headline else None,
+                "traffic_source": "constant: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full "
+                                  "capture of this command (profiles/), not measured live" if headline else None,
                 "peak_source": peaks["src"] + " bf16 sustained (kernel timed inside a long step)",
-                "operand_format": {"tc": "split-fp16 hi/lo, 3 tcgen05.mma products per algorithmic product (fp32-class accuracy); "
-                                         "the algorithmic fraction is therefore bounded by 1/3 of the bf16 peak",
+                "operand_format": {"tc": "split-fp16 hi/lo operands on tcgen05, fp32 accumulate in TMEM (fp32-class accuracy); several MMA "
+                                         "products are issued per algorithmic product (see issued_mma_tflops)",
                                    "fp32": "fp32 FFMA (CUDA cores)", "fp64": "fp64 DFMA"}[prec],
                 "algorithmic_flops_per_launch": kern[dom][1], "ms_per_launch": per_launch[dom], "launches_per_step": kern[dom][2],
                 "issued_mma_tflops": ({k: issued[k] / (med[k] * 1e-3) / 1e12 for k in kern if med.get(k, 0) > 0} if prec == "tc" else None),
+                "mma_products_per_algorithmic_product": passes if prec == "tc" else None,
                 "all_kernels": {kern[k][0].split(" ")[0]: {"ms_per_launch": per_launch[k], "launches": kern[k][2],
-                                                            "achieved_TFLOPs": kern[k][1] / (per_launch[k] * 1e-3) / 1e12 if per_launch[k] > 0 else 0.0}
+                                                            "achieved_TFLOPs": kern[k][1] / (per_launch[k] * 1e-3) / 1e12 if per_launch[k] > 0 else 0.0,
+                                                            "frac": (kern[k][1] / (per_launch[k] * 1e-3) / 1e12 / peaks["tc"]) if per_launch[k] > 0 else 0.0}
                                 for k in kern},
                 "step_algorithmic_tflops": work["flops_full"] / (ms_step * 1e-3) / 1e12,
+                "step_frac": work["flops_full"] / (ms_step * 1e-3) / 1e12 / peaks["tc"],
                 "hbm_view": {"achieved_GBps": work["bytes"] / (n_kernel_ms * 1e-3) / 1e9, "peak_GBps": peaks["hbm"],
                              "frac": work["bytes"] / (n_kernel_ms * 1e-3) / 1e9 / peaks["hbm"],
                              "note": "path is a dense contraction (2 M^2 flops per 16 B row): not HBM-bound for M >~ 3 (SURVEY 8d)"},
                 "phase_ms_median": med}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        cpu = cpu_baseline(args.config, args.cpu_rows, steps=1)
+        cpu = cpu_baseline(synth, args.config, args.cpu_rows, reps=1)
     line = {"metric": "ELBO steps/sec (ELBO + all gradients)", "value": 1e3 / ms_step, "unit": "ELBO steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": {"tc": "f16x3 (split fp16 on tcgen05, fp32 accumulate; fp64 M x M algebra)", "fp32": "f32", "fp64": "f64"}[prec],
+            "scaling": "strong", "vs_baseline": None, "dtype": {"tc": "f16x2 split (fp16 hi/lo on tcgen05, fp32 accumulate; fp64 M x M algebra)", "fp32": "f32", "fp64": "f64"}[prec],
             "data": "synthetic", "config": workload_config(args, c), "elbo": elbo_resident, "clocks": clocks,
-            "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": wall}
+            "gpu_launches": launches, "optimizer": None if opt is None else {"kind": "Adadelta (climin semantics), device-resident", "flat_size": n_opt},
+            "e2e": e2e, "e2e_pageable": e2e_pageable, "variants": variants, "parity": parity,
+            "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": wall}
     print(json.dumps(line))
+    if opt is not None:
+        lib.hmogp_opt_destroy(opt)
     if world > 1:
         dist.destroy_process_group()
 

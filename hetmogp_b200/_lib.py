@@ -51,6 +51,11 @@ class Status(C.Structure):
                 ("n_negative_v", C.c_int64)]
 
 
+class OptSegment(C.Structure):
+    _fields_ = [("offset", C.c_int64), ("count", C.c_int64), ("param", C.c_void_p), ("grad", C.c_void_p),
+                ("stride", C.c_int32), ("positive", C.c_int32), ("variational", C.c_int32), ("reserved", C.c_int32)]
+
+
 class LinAlgError(np.linalg.LinAlgError):
     """jitchol gave up (GPy raises numpy.linalg.LinAlgError; reference util.py:198)."""
 
@@ -85,6 +90,7 @@ def _load():
         "hmogp_step_finish": (C.c_int, [vp, vp, C.POINTER(Grads), i32, i32, C.POINTER(Status)]),
         "hmogp_inference_host": (C.c_int, [C.POINTER(Config), C.POINTER(vp), C.POINTER(vp), c_int64_p,
                                            C.POINTER(Params), C.POINTER(Grads), i32, C.POINTER(Status)]),
+        "hmogp_predict_f": (C.c_int, [vp, C.POINTER(Params), i32, i32, vp, i64, vp, vp]),
         "hmogp_get_rows": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
         "hmogp_get_dL_dKmn": (C.c_int, [vp, i32, i32, vp, vp]),
         "hmogp_get_kuu": (C.c_int, [vp, vp, vp, vp]),
@@ -95,6 +101,15 @@ def _load():
         "hmogp_enable_timing": (C.c_int, [vp, i32]),
         "hmogp_last_timing": (C.c_int, [vp, C.POINTER(C.c_float), c_int32_p]),
         "hmogp_tc_built": (C.c_int, []),
+        "hmogp_opt_create": (C.c_int, [i32, C.POINTER(OptSegment), i32, C.c_double, C.c_double, C.c_double, C.c_double,
+                                       C.POINTER(vp)]),
+        "hmogp_opt_destroy": (None, [vp]),
+        "hmogp_opt_size": (i64, [vp]),
+        "hmogp_opt_state": (vp, [vp, i32]),
+        "hmogp_opt_get_state": (C.c_int, [vp, i32, vp, vp]),
+        "hmogp_opt_gather": (C.c_int, [vp, vp]),
+        "hmogp_opt_lookahead": (C.c_int, [vp, i32, vp]),
+        "hmogp_opt_update": (C.c_int, [vp, i32, i32, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch

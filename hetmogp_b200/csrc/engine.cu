@@ -356,6 +356,27 @@ __global__ void extract_mm_kernel(const double* src, double* dst, int M, int Mp,
     dst[((int64_t)q * M + i) * M + j] = (lower_only && j > i) ? 0.0 : src[((int64_t)q * Mp + i) * Mp + j];
 }
 
+// W-mix only (svmogp_inf.py:216-218 via SURVEY App. B): m_fd = sum_q W_dq a_q, v_fd = kdiag_d + sum_q W_dq^2 c_q for the F
+// output functions of one task, from the per-row projections (SoA: array k at k * cap).  Prediction path: no likelihood.
+template <typename T>
+__global__ void mix_rows_kernel(const void* AC, int64_t cap, int64_t n, int Q, int foff, int F, const HmConsts* cs,
+                                double* m_out, double* v_out) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const T* ac = reinterpret_cast<const T*>(AC) + row;
+    for (int f = 0; f < F; ++f) {
+        const int d = foff + f;
+        double mm = 0.0, vv = cs->kdiag[d];
+        for (int q = 0; q < Q; ++q) {
+            const double w = cs->W[d][q];
+            mm += w * (double)ac[(size_t)q * cap];
+            vv += w * w * (double)ac[(size_t)(Q + q) * cap];
+        }
+        m_out[row * F + f] = mm;
+        v_out[row * F + f] = vv;
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ engine state
@@ -412,6 +433,7 @@ struct hmogp_engine {
     double *o_lm, *o_VE, *o_KL, *o_dmu, *o_dL, *o_dKmm, *o_drbf, *o_dW, *o_dkappa, *o_dZ;
     // status
     double jitter_h[HM_MAXQ];
+    int chol_fail_h[HM_MAXQ];   // factorisation attempts of K_uu^q that failed in the last prepare (jitchol retries)
     bool has_chain;
     int last_what;
     // timing
@@ -545,7 +567,7 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
     // K_uu, jitchol (util.py:197-198): no jitter unless the plain factorisation fails; then var*1e-6 * 10^k, k<5
     double var_h[HM_MAXQ];
     bool have_var = false;
-    for (int q = 0; q < Q; ++q) e->jitter_h[q] = 0.0;
+    for (int q = 0; q < Q; ++q) { e->jitter_h[q] = 0.0; e->chol_fail_h[q] = 0; }
     for (int attempt = 0;; ++attempt) {
         HM_CUDA(cudaMemcpyAsync(e->jitter_d, e->jitter_h, sizeof(double) * Q, cudaMemcpyHostToDevice, s));
         HM_CHECK(hm_build_kuu(s, e->Zp, e->consts, e->jitter_d, e->Kuu, M, Mp, Xd, Q));
@@ -557,7 +579,7 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
         if (!HM_SKIP(64)) HM_CUDA(cudaStreamSynchronize(s));
         bool any = false;
         if (HM_SKIP(64)) for (int q = 0; q < Q; ++q) fl[q] = 0;
-        for (int q = 0; q < Q; ++q) any = any || fl[q];
+        for (int q = 0; q < Q; ++q) { any = any || fl[q]; if (fl[q]) ++e->chol_fail_h[q]; }
         if (!any) break;
         if (attempt >= 5) {
             cudaStreamSynchronize(s2);
@@ -1161,6 +1183,7 @@ int hmogp_step_finish(hmogp_engine* e, const double* stats_dev, hmogp_grads* g, 
         memset(status, 0, sizeof(*status));
         for (int q = 0; q < Q; ++q) {
             status->jitter[q] = e->jitter_h[q];
+            status->chol_fail[q] = e->chol_fail_h[q];
             status->lu_singular[q] = fl[q];
         }
         for (int t = 0; t < e->T; ++t) status->n_negative_v += (int64_t)nneg[t];
@@ -1187,6 +1210,51 @@ int hmogp_inference_host(const hmogp_config* cfg, const double* const* X, const 
     for (int t = 0; t < cfg->T && !rc; ++t) rc = hmogp_set_data(e, t, X[t], Y[t], N[t], HMOGP_MEM_HOST);
     if (!rc) rc = hmogp_elbo_and_grads(e, p, g, HMOGP_MEM_HOST, what, status);
     hmogp_destroy(e);
+    return rc;
+}
+
+int hmogp_predict_f(hmogp_engine* e, const hmogp_params* p, int32_t mem_kind, int32_t t, const double* Xnew, int64_t N,
+                    double* m_fd, double* v_fd) {
+    if (!e || !p || t < 0 || t >= e->T || N < 0 || (N > 0 && (!Xnew || !m_fd || !v_fd))) { hm_set_error("hmogp_predict_f: bad argument"); return HMOGP_ERR_ARG; }
+    if (!p->Z || !p->m_u || !p->L_u || !p->rbf_var || !p->rbf_ls || !p->W || !p->kappa) { hm_set_error("hmogp_predict_f: null parameter"); return HMOGP_ERR_ARG; }
+    if (N == 0) return 0;
+    HM_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    HM_CHECK(mm_prepare(e, p, mem_kind));
+    const int F = e->tk.dimf[t];
+    const bool host = mem_kind == HMOGP_MEM_HOST;
+    double *xd = nullptr, *md = nullptr, *vd = nullptr;
+    void* ac = nullptr;
+    int rc = 0;
+    auto fail = [&](const char* what) { hm_set_error("hmogp_predict_f: %s: %s", what, cudaGetErrorString(cudaGetLastError())); return HMOGP_ERR_CUDA; };
+    if (host) {
+        if (cudaMalloc((void**)&xd, sizeof(double) * N * e->Xd) != cudaSuccess || cudaMalloc((void**)&md, sizeof(double) * N * F) != cudaSuccess ||
+            cudaMalloc((void**)&vd, sizeof(double) * N * F) != cudaSuccess) rc = fail("cudaMalloc");
+        if (!rc && cudaMemcpyAsync(xd, Xnew, sizeof(double) * N * e->Xd, cudaMemcpyHostToDevice, s) != cudaSuccess) rc = fail("upload");
+    } else { xd = const_cast<double*>(Xnew); md = m_fd; vd = v_fd; }
+    if (!rc && cudaMalloc(&ac, (size_t)N * e->tk.acs * esize(e->prec)) != cudaSuccess) rc = fail("cudaMalloc");
+    if (!rc) {
+        // a one-task view of the task table: only task t has rows, and they are the new inputs
+        HmTasks tk = e->tk;
+        for (int u = 0; u < e->T; ++u) { tk.count[u] = 0; tk.begin[u] = 0; }
+        tk.X[t] = xd; tk.Y[t] = nullptr; tk.count[t] = N; tk.AC[t] = ac; tk.MW[t] = nullptr; tk.cap[t] = N;
+        HmProjArgs pa = proj_args(e);
+        if (e->prec == HMOGP_PREC_TC) rc = hm_tc_proj_fwd(s, tk, pa, e->Cb, e->tcinfo, false, e->tc_npass, e->tc_ncta);
+        else rc = hm_proj_fwd(s, e->prec, tk, pa);
+        if (!rc) {
+            const unsigned nb = (unsigned)hm_cdiv(N, 256);
+            if (e->prec == HMOGP_PREC_FP64) mix_rows_kernel<double><<<nb, 256, 0, s>>>(ac, N, N, e->Q, e->tk.foff[t], F, e->consts, md, vd);
+            else mix_rows_kernel<float><<<nb, 256, 0, s>>>(ac, N, N, e->Q, e->tk.foff[t], F, e->consts, md, vd);
+            if (cudaGetLastError() != cudaSuccess) rc = fail("mix_rows_kernel");
+        }
+        if (!rc && host) {
+            if (cudaMemcpyAsync(m_fd, md, sizeof(double) * N * F, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                cudaMemcpyAsync(v_fd, vd, sizeof(double) * N * F, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = fail("download");
+        }
+    }
+    if (cudaStreamSynchronize(s) != cudaSuccess && !rc) rc = fail("sync");
+    if (host) { cudaFree(xd); cudaFree(md); cudaFree(vd); }
+    cudaFree(ac);
     return rc;
 }
 

@@ -14,6 +14,8 @@ from ._lib import lib, check, f64, ptr
 
 
 class Engine(object):
+    MAX_PINNED_SETS = 8   # page-locked result sets per output signature; further live sets use pageable memory
+
     def __init__(self, lik_specs, M, Q, Xdim, precision="fp32", device=0, group=None):
         self.lik_specs = [tuple(s) for s in lik_specs]
         self.T = len(self.lik_specs)
@@ -35,7 +37,7 @@ class Engine(object):
         self.N = [0] * self.T
         self.status = None
         self._stats = None
-        self._host_out = {}    # page-locked output buffers of the host path, two alternating sets per output signature
+        self._host_out = {}    # pools of page-locked result buffer sets, per output signature (see _alloc_out)
 
     # ------------------------------------------------------------------ life cycle
     def close(self):
@@ -115,18 +117,26 @@ class Engine(object):
         if on_device:
             out = {k: torch.empty(s, dtype=torch.float64, device="cuda:%d" % self.device) for k, s in shapes.items()}
         else:
-            # Host results land in page-locked buffers owned by the engine (a device-to-host copy into pageable memory is
-            # staged by the driver at a fifth of the speed: 1 ms of a 48 ms step for the 9 MB of cfg3).  Two sets alternate,
-            # so the arrays of a call stay valid until the call after the next one; copy them to keep them longer.
+            # Host results land in page-locked buffers (a device-to-host copy into pageable memory is staged by the driver
+            # at a fifth of the speed: 1 ms of a 48 ms step for the 9 MB of cfg3).  The returned numpy arrays are views of
+            # a pooled buffer set and own it for as long as any of them (or a slice of them) is referenced: a set is
+            # handed out again only when the caller has dropped every array of it, so results never alias a later call's
+            # (the reference returns fresh arrays, svmogp_inf.py:107-109).
+            import sys
             key = (what, bool(want_dKmm))
-            ring = self._host_out.setdefault(key, {"sets": [], "next": 0})
-            if len(ring["sets"]) < 2:
-                ring["sets"].append({k: torch.empty(s, dtype=torch.float64, pin_memory=True) for k, s in shapes.items()})
-                pinned = ring["sets"][-1]
-            else:
-                pinned = ring["sets"][ring["next"]]
-                ring["next"] ^= 1
-            out = {k: v.numpy() for k, v in pinned.items()}
+            pool = self._host_out.setdefault(key, [])
+            pinned = None
+            for cand in pool:
+                # a master array is free when nothing but the pool refers to it (every numpy view of it, and every
+                # slice of a view, has it as .base): the dict entry, the loop variable, the argument of getrefcount
+                if all(sys.getrefcount(m) <= 3 for m in cand.values()):
+                    pinned = cand
+                    break
+            if pinned is None:
+                pin = len(pool) < self.MAX_PINNED_SETS
+                pinned = {k: torch.empty(s, dtype=torch.float64, pin_memory=pin).numpy() for k, s in shapes.items()}
+                pool.append(pinned)
+            out = {k: m.view() for k, m in pinned.items()}
         gs = _lib.Grads()
         for k, a in out.items():
             setattr(gs, k, ptr(a))
@@ -136,8 +146,8 @@ class Engine(object):
         """params: dict with Z, m_u, L_u, rbf_var, rbf_ls, W, kappa [, W_chain, kappa_chain, batch_scale] as numpy
         arrays (host path: copies inside the call) or torch CUDA tensors (device path).  Returns a dict of outputs
         in the reference's layouts (see include/hetmogp_b200.h); ``self.status`` holds the flags.  With host parameters the
-        returned numpy arrays are views of page-locked buffers owned by the engine (two alternating sets): they stay valid
-        until the call after the next one -- copy what must live longer."""
+        returned numpy arrays are backed by pooled page-locked buffers that stay theirs for as long as they are referenced
+        (no aliasing between calls)."""
         w = {"elbo": _lib.WHAT_ELBO, "ve": _lib.WHAT_VE, "full": _lib.WHAT_FULL}[what] if isinstance(what, str) else what
         on_device = hasattr(params["m_u"], "data_ptr")
         kind = _lib.MEM_DEVICE if on_device else _lib.MEM_HOST
@@ -158,16 +168,40 @@ class Engine(object):
             if self._stats is None:
                 n = int(lib.hmogp_stats_len(self._h))
                 self._stats = torch.empty(n, dtype=torch.float64, device="cuda:%d" % self.device)
-                self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+            # the all-reduce runs on torch's current stream: keep the engine on the same one, every call
+            self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
             check(lib.hmogp_step_local(self._h, C.byref(ps), kind, w, C.c_void_p(self._stats.data_ptr())))
             dist.all_reduce(self._stats, op=dist.ReduceOp.SUM, group=self.group)   # the ONE collective of a step
             check(lib.hmogp_step_finish(self._h, C.c_void_p(self._stats.data_ptr()), C.byref(gs), kind, w, C.byref(st)))
         self.status = {"jitter": [st.jitter[q] for q in range(self.Q)],
+                       "chol_fail": [st.chol_fail[q] for q in range(self.Q)],
                        "lu_singular": [st.lu_singular[q] for q in range(self.Q)],
                        "n_negative_v": int(st.n_negative_v)}
         if self.status["n_negative_v"] > 0:
             print('v negative!')   # svmogp_inf.py:221-222 (warning only)
         return out
+
+    def predict_f(self, params, t, Xnew):
+        """q(f_d) at new inputs for the output functions of task t: (m_fd, v_fd), each (N, dim_f[t]) -- the forward
+        projection and the W-mix only, no labels, no likelihood (hmogp_predict_f)."""
+        keep = []
+        ps = self._params(params, keep)
+        if isinstance(Xnew, np.ndarray) or not hasattr(Xnew, "data_ptr"):
+            x = f64(Xnew).reshape(-1, self.Xdim)
+            n = int(x.shape[0])
+            m, v = np.empty((n, self.dimf[t])), np.empty((n, self.dimf[t]))
+            kind = _lib.MEM_HOST
+        else:
+            import torch
+            x = Xnew.contiguous().reshape(-1, self.Xdim)
+            n = int(x.shape[0])
+            m = torch.empty((n, self.dimf[t]), dtype=torch.float64, device=x.device)
+            v = torch.empty_like(m)
+            kind = _lib.MEM_DEVICE
+        if (kind == _lib.MEM_DEVICE) != hasattr(params["m_u"], "data_ptr"):
+            raise ValueError("predict_f: parameters and Xnew must both be host arrays or both CUDA tensors")
+        check(lib.hmogp_predict_f(self._h, C.byref(ps), kind, int(t), ptr(x), n, ptr(m), ptr(v)))
+        return m, v
 
     # ------------------------------------------------------------------ introspection (tests, small N)
     def rows(self, t):

@@ -9,6 +9,8 @@ import random
 import numpy as np
 
 from .gpy_shim import RBF, Coregionalize
+from .toy import true_u_functions, true_f_functions, generate_toy_U   # noqa: F401  (util.py:21-50,202-206)
+from .vem import vem_algorithm                                          # noqa: F401  (util.py:284-331)
 
 
 def get_batch_scales(X_all, X):                                             # util.py:15-19
@@ -16,10 +18,11 @@ def get_batch_scales(X_all, X):                                             # ut
 
 
 def mini_slices(n_samples, batch_size):                                     # util.py:52-60 (bit-exact slice bounds)
+    """The last slice is NOT clamped to n_samples (util.py:60): indexing clamps it, the bounds themselves do not."""
     n_batches, rest = divmod(n_samples, batch_size)
     if rest != 0:
         n_batches += 1
-    return [slice(i * batch_size, min((i + 1) * batch_size, n_samples)) for i in range(n_batches)]
+    return [slice(i * batch_size, (i + 1) * batch_size) for i in range(n_batches)]
 
 
 def draw_mini_slices(n_samples, batch_size, with_replacement=False):        # util.py:62-72
@@ -70,3 +73,4 @@ def LCM(input_dim, output_dim, kernels_list, W_list, kappa_list, rank, name='B_q
         K.append(Kq)
         B_q.append(Bq)
     return K, B_q
+

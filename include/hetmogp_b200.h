@@ -56,7 +56,7 @@ extern "C" {
 /* arithmetic of the N-sized kernels (the M x M algebra is always fp64) */
 #define HMOGP_PREC_FP64 0 /* SIMT fp64 everywhere: reference-grade parity mode            */
 #define HMOGP_PREC_FP32 1 /* SIMT fp32 tiles, fp64 reductions                              */
-#define HMOGP_PREC_TC 2   /* tcgen05 tensor-core tiles (split-bf16 operands, fp32 TMEM acc) */
+#define HMOGP_PREC_TC 2   /* tcgen05 tensor-core tiles (split-fp16 operands, fp32 TMEM acc) */
 
 /* what a step computes */
 #define HMOGP_WHAT_ELBO 0 /* ELBO only                                                  */
@@ -109,7 +109,7 @@ typedef struct {
 } hmogp_grads;
 
 typedef struct {
-    int32_t chol_fail[HMOGP_MAX_Q];  /* 1 if K_uu^q was not PD on the last attempt            */
+    int32_t chol_fail[HMOGP_MAX_Q];  /* failed Cholesky attempts of K_uu^q (jitchol retries; 0 = PD as is) */
     double jitter[HMOGP_MAX_Q];      /* jitter finally added to K_uu^q (0 = none; jitchol)     */
     int32_t lu_singular[HMOGP_MAX_Q];/* 1 if S_q^-1 contains inf (svmogp_inf.py:126)           */
     int64_t n_negative_v;            /* rows with v_fd < 0 ('v negative!', svmogp_inf.py:221)  */
@@ -158,6 +158,12 @@ int hmogp_step_finish(hmogp_engine* e, const double* stats_dev, hmogp_grads* g, 
 int hmogp_inference_host(const hmogp_config* cfg, const double* const* X, const double* const* Y, const int64_t* N,
                          const hmogp_params* p, hmogp_grads* g, int32_t what, hmogp_status* status);
 
+/* ---- prediction: q(f_d) at new inputs from q(U) (the O(M^2)-per-point route to what svmogp.py:263-370 obtains through
+ *      inference(..., predictive=True), svmogp_inf.py:43-50,216-218): m_fd, v_fd [N, dim_f(t)] for the output functions
+ *      of task t at Xnew [N, Xdim].  No labels are needed and no likelihood is evaluated.  Pointers per mem_kind. ---- */
+int hmogp_predict_f(hmogp_engine* e, const hmogp_params* p, int32_t mem_kind, int32_t t, const double* Xnew, int64_t N,
+                    double* m_fd, double* v_fd);
+
 /* ---- per-row intermediates of the last evaluation (tests; small N) ---- */
 /* m_fd, v_fd: [N_t, dim_f];  VE: [N_t];  dm, dv: [N_t, dim_f]  (svmogp_inf.py:54-78). Host pointers. */
 int hmogp_get_rows(hmogp_engine* e, int32_t t, double* m_fd, double* v_fd, double* VE, double* dm, double* dv);
@@ -179,6 +185,38 @@ int hmogp_lik_pointwise(const hmogp_lik_desc* lik, int64_t N, const double* F, c
  *      svmogp_inf.py:118,176-178).  flat [M(M+1)/2, D], dense [D, M, M]. ---- */
 int hmogp_flat_to_triang(const double* flat, double* dense, int32_t M, int32_t D, int32_t mem_kind, void* cuda_stream);
 int hmogp_triang_to_flat(const double* dense, double* flat, int32_t M, int32_t D, int32_t mem_kind, void* cuda_stream);
+
+/* ---- on-device optimiser step of the stochastic loop: climin.Adadelta(model.optimizer_array, model.stochastic_grad,
+ *      step_rate, momentum=0.9) of util.py:320-329 over paramz' flat optimizer_array (link order svmogp.py:71-75, Logexp
+ *      transform of the positive parameters), with the VE / VM gradient gating of svmogp.py:104-166.  Parameters and
+ *      gradients are the device arrays a step reads / writes (hmogp_params / hmogp_grads with HMOGP_MEM_DEVICE), so a
+ *      training iteration never leaves the GPU. ---- */
+#define HMOGP_OPT_MAX_SEGMENTS 64
+typedef struct {
+    int64_t offset;      /* first position in the flat vector (segments are contiguous, in link order)      */
+    int64_t count;       /* elements                                                                         */
+    double* param;       /* device array holding the (constrained) parameter; element k at param[k*stride]   */
+    const double* grad;  /* device array holding dELBO/dparam, same indexing                                 */
+    int32_t stride;      /* 1, or Q for the columns of W / kappa [J, Q]                                      */
+    int32_t positive;    /* 1: Logexp-transformed (variance, lengthscale, kappa)                             */
+    int32_t variational; /* 1: m_u / L_u (gradient live in VE steps); 0: Z, kernels, B (live in VM steps)    */
+    int32_t reserved;
+} hmogp_opt_segment;
+typedef struct hmogp_opt hmogp_opt;
+int hmogp_opt_create(int32_t device, const hmogp_opt_segment* segs, int32_t nseg, double step_rate, double decay,
+                     double momentum, double offset, hmogp_opt** out);
+void hmogp_opt_destroy(hmogp_opt* o);
+int64_t hmogp_opt_size(const hmogp_opt* o);
+/* device pointers of the state vectors: 0 wrt (the flat optimizer_array), 1 gms, 2 sms, 3 step */
+double* hmogp_opt_state(hmogp_opt* o, int32_t which);
+/* copy a state vector ([hmogp_opt_size] doubles) to host memory */
+int hmogp_opt_get_state(hmogp_opt* o, int32_t which, double* host_out, void* cuda_stream);
+/* wrt <- unconstrained(parameters): model.optimizer_array */
+int hmogp_opt_gather(hmogp_opt* o, void* cuda_stream);
+/* wrt -= momentum * step (if apply_momentum), parameters <- constrained(wrt): model.optimizer_array = wrt */
+int hmogp_opt_lookahead(hmogp_opt* o, int32_t apply_momentum, void* cuda_stream);
+/* g = -transformed gradient (zero where gated off), then the Adadelta update; grad_out [n] receives g (or NULL) */
+int hmogp_opt_update(hmogp_opt* o, int32_t ve_active, int32_t vm_active, double* grad_out, void* cuda_stream);
 
 /* ---- timing hooks for bench.py: CUDA-event time (ms) and launch count of the N-sized kernels of the
  *      last evaluation, measured on the engine's stream. ---- */

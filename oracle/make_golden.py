@@ -114,8 +114,50 @@ def likelihood_golden():
     return out
 
 
+STREAM_CASES = [(200, 50), (203, 50), (7, 3), (5, 8), (1000, 64), (64, 64)]      # (n_samples, batch_size)
+
+
+def util_golden():
+    """Host helpers of hetmogp/util.py that produce integer / seeded outputs: the minibatch slice stream (util.py:52-72,
+    two epochs), get_batch_scales (util.py:15-19), random_W_kappas (util.py:92-104) and the toy generators
+    (util.py:21-50, 202-206) under fixed numpy seeds."""
+    ns = verbatim.load()
+    u = ns.util
+    out = {}
+    for n, bs in STREAM_CASES:
+        sl = u.mini_slices(n, bs)
+        out["mini_%d_%d" % (n, bs)] = np.array([[s.start, s.stop] for s in sl], dtype=np.int64)
+        gen = u.draw_mini_slices(n, bs)
+        seq = [next(gen) for _ in range(2 * len(sl) + 1)]
+        out["draw_%d_%d" % (n, bs)] = np.array([[s.start, s.stop] for s in seq], dtype=np.int64)
+        X = np.zeros((n, 1))
+        out["len_%d_%d" % (n, bs)] = np.array([X[s].shape[0] for s in seq], dtype=np.int64)
+        out["scale_%d_%d" % (n, bs)] = np.array([u.get_batch_scales([X], [X[s]])[0] for s in seq if X[s].shape[0] > 0])
+    np.random.seed(101)
+    W_list, kappa_list = u.random_W_kappas(3, 5, rank=1)
+    out["rwk_W"] = np.hstack(W_list)
+    out["rwk_kappa"] = np.stack(kappa_list, axis=1)
+    np.random.seed(102)
+    Xl = [np.linspace(0, 1, 17)[:, None], np.linspace(-1, 2, 9)[:, None]]
+    tu = u.true_u_functions(Xl, 3)
+    out["true_u_0"], out["true_u_1"] = tu[0], tu[1]
+    liks = [verbatim.make_likelihood(ns, s) for s in (("HetGaussian",), ("Bernoulli",))]
+    meta = ns.HetLikelihood(liks).generate_metadata()
+    np.random.seed(103)
+    W_list, _ = u.random_W_kappas(3, 3, rank=1)
+    tf = u.true_f_functions(tu, W_list, 3, liks, meta)
+    out["true_f_W"] = np.hstack(W_list)
+    out["true_f_0"], out["true_f_1"] = tf[0], tf[1]
+    np.random.seed(104)
+    out["toy_U"] = u.generate_toy_U(np.linspace(0, 1, 11)[:, None], 4)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "util_streams.npz"), **out)
+    return out
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    o = util_golden()
+    print("util_streams: %d arrays" % len(o))
     for name, case in INFERENCE_CASES.items():
         o = inference_golden(name, case)
         print("inference_%s: log_marginal = %.12g" % (name, o["log_marginal"][0, 0]))
