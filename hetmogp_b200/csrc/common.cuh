@@ -149,6 +149,6 @@ int hm_tc_gram(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const HmT
 int hm_tc_gram2(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const HmTcInfo* info, const HmGramSeg* segs,
                 const int* seg_off, int nV, double* slots, int npairs, int f1, int f2, int npass);
 int hm_tc_gram2_reduce(cudaStream_t s, const double* slots, const HmGramJob* jobs, const int2* jobslots, int njobs, int Q, int nV,
-                       double* H, double* g0, int M, int Mp);
+                       double* H, double* g0, int M, int Mp, int npass);
 int hm_tc_gram_reduce(cudaStream_t s, const double* slots, const HmGramJob* jobs, const int2* jobslots, int njobs, int Q,
                       const HmGramWeights& gw, double* H, double* g0, int64_t gstride, int M, int Mp);

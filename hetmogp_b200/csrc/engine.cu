@@ -761,7 +761,7 @@ int tc_backward(hmogp_engine* e, int what, double* stats) {
     HM_CUDA(cudaMemsetAsync(stats + e->off_H, 0, sizeof(double) * MM, s));
     if (e->gram2) {
         HM_CHECK(hm_tc_gram2(s, e->tk, pa, e->tcinfo, e->segs_d, e->segoff_d, gw.nV, e->slots, e->nworkers / 2, e->tc_f1, e->tc_f2, e->tc_npass));
-        HM_CHECK(hm_tc_gram2_reduce(s, e->slots, e->jobs_d, e->jobslots_d, (int)e->jobs_h.size(), Q, gw.nV, stats + e->off_H, e->gvec, M, Mp));
+        HM_CHECK(hm_tc_gram2_reduce(s, e->slots, e->jobs_d, e->jobslots_d, (int)e->jobs_h.size(), Q, gw.nV, stats + e->off_H, e->gvec, M, Mp, e->tc_npass));
     } else {
         HM_CHECK(hm_tc_gram(s, e->tk, pa, e->tcinfo, e->segs_d, e->segoff_d, gw, e->slots, e->nworkers, e->tc_f1, e->tc_f2, e->tc_npass));
         HM_CHECK(hm_tc_gram_reduce(s, e->slots, e->jobs_d, e->jobslots_d, (int)e->jobs_h.size(), Q, gw, stats + e->off_H, e->gvec, gstride, M, Mp));
@@ -883,7 +883,7 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
         e->gram2 = !(eg && atoi(eg) == 1) && e->Mc % 256 == 0 && e->nworkers >= 2;
         e->gram_chunk = e->gram2 ? HM_GRAM2_CHUNK : HM_GRAM_CHUNK;
         eg = getenv("HMOGP_TC_GRAM_DIAG_COST");
-        e->gram2_cost_diag = eg ? atoi(eg) : 75;
+        e->gram2_cost_diag = eg ? atoi(eg) : 75;   // a diagonal block generates one operand tile instead of two (generation, not the MMAs, sets the pace)
         e->tc_f1 = (ev ? atoi(ev) : 512) / e->gram_chunk;
         if (e->tc_f1 < 1) e->tc_f1 = 1;
         ev = getenv("HMOGP_TC_FLUSH3_ROWS");         // rows between fp64 flushes

@@ -10,9 +10,12 @@
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------------ GEMM
-// C = alpha * op(A) op(B) + beta * C ; 64x64x16 tiles, 256 threads, 4x4 register tile; the next k-tile is fetched from
-// global memory (128-bit loads) into registers while the current one is multiplied out of shared memory.  M, N multiples
-// of 4, K a multiple of 16 (every call site: padded M, 64 * 2^k blocks, 32-wide Cholesky panels).
+// C = alpha * op(A) op(B) + beta * C ; 64x64x16 tiles, 256 threads = 8 warps of 32 x 16 outputs on the fp64 tensor
+// cores (mma.sync m8n8k4: 4 x 2 blocks per warp, fragments read from the k-major shared-memory tiles with conflict-free
+// 64-bit loads; the 4 x 4 DFMA register tile this replaces spent two shared-memory wavefronts per FMA-cycle and ran at
+// 16 % of the fp64 rate).  The next k-tile is fetched from global memory (128-bit loads) into registers while the current
+// one is multiplied.  M, N multiples of 4, K a multiple of 16 (every call site: padded M, 64 * 2^k blocks, 32-wide
+// Cholesky panels).
 // flags (HM_GEMM_*): LOWER  only tiles on or below the block diagonal;  MIRROR  LOWER + the transposed tile is written
 // too (symmetric products);  K_GE / K_LE / KB_GE  restrict the k range of a tile to where triangular operands are non-zero.
 template <bool TA, bool TB>
@@ -70,11 +73,14 @@ __global__ void __launch_bounds__(256) dgemm_kernel(int M, int N, int K, double 
             *reinterpret_cast<double2*>(&Bs[bk][bj + 2]) = rb1;
         }
     };
-    double acc[4][4];
+    // warp tile: rows [wm * 32, +32) x columns [wn * 16, +16) of the CTA tile, as 4 x 2 blocks of m8n8
+    const int warp = tid >> 5, lane = tid & 31, wm = warp & 1, wn = warp >> 1;
+    const int fr = lane >> 2, fk = lane & 3;          // fragment coordinates: A[row fr][k fk], B[k fk][col fr]
+    double acc[4][2][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     if (kbeg < kend) fetch(kbeg);
     for (int k0 = kbeg; k0 < kend; k0 += BK) {
@@ -82,33 +88,39 @@ __global__ void __launch_bounds__(256) dgemm_kernel(int M, int N, int K, double 
         __syncthreads();
         if (k0 + BK < kend) fetch(k0 + BK);
 #pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            const double2 a01 = *reinterpret_cast<const double2*>(&As[kk][ty * 4]);
-            const double2 a23 = *reinterpret_cast<const double2*>(&As[kk][ty * 4 + 2]);
-            const double2 b01 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4]);
-            const double2 b23 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4 + 2]);
-            const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+        for (int kk = 0; kk < BK; kk += 4) {
+            double a[4], b[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk + fk][wm * 32 + i * 8 + fr];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) b[j] = Bs[kk + fk][wn * 16 + j * 8 + fr];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 2; ++j)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                                 : "d"(a[i]), "d"(b[j]));
         }
         __syncthreads();
     }
     const bool mirror = (flags & HM_GEMM_MIRROR) && blockIdx.x != blockIdx.y;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int gi = row0 + ty * 4 + i;
+        const int gi = row0 + wm * 32 + i * 8 + fr;
         if (gi >= M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gj = col0 + tx * 4 + j;
-            if (gj >= N) continue;
-            double* c = C + (int64_t)gi * ldc + gj;
-            double v = alpha * acc[i][j];
-            if (beta != 0.0) v += beta * (*c);
-            *c = v;
-            if (mirror) C[(int64_t)gj * ldc + gi] = v;
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gj = col0 + wn * 16 + j * 8 + 2 * fk + e;
+                if (gj >= N) continue;
+                double* c = C + (int64_t)gi * ldc + gj;
+                double v = alpha * acc[i][j][e];
+                if (beta != 0.0) v += beta * (*c);
+                *c = v;
+                if (mirror) C[(int64_t)gj * ldc + gi] = v;
+            }
         }
     }
 }
@@ -153,35 +165,35 @@ __global__ void __launch_bounds__(128) chol_panel_kernel(double* A, int ld, int6
     }
     __syncthreads();
     if (tid < 32) {
+        // Right-looking factorisation of the 32 x 32 diagonal block with lane = row and the row held in registers: per
+        // pivot one shuffle (a_jj), one reciprocal square root, the scaled column through shared memory, and a rank-one
+        // update of the trailing row entries (broadcast loads + FMAs, independent of each other).  The left-looking
+        // version this replaces walked a dependent chain of shared-memory dot products per pivot (~25 us per panel,
+        // 16 panels: the largest item of the M-sized serial chain).
         const int lane = tid;
+        double a[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) a[j] = D[lane][j];
+        __shared__ double colj[NB];
+#pragma unroll
         for (int j = 0; j < NB; ++j) {
-            double sacc = 0.0;
-            if (lane >= j) {   // four independent partial sums: the dependent chain is j / 4 FMAs instead of j
-                double s0 = D[lane][j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                int l = 0;
-                for (; l + 4 <= j; l += 4) {
-                    s0 -= D[lane][l] * D[j][l];
-                    s1 -= D[lane][l + 1] * D[j][l + 1];
-                    s2 -= D[lane][l + 2] * D[j][l + 2];
-                    s3 -= D[lane][l + 3] * D[j][l + 3];
-                }
-                for (; l < j; ++l) s0 -= D[lane][l] * D[j][l];
-                sacc = (s0 + s1) + (s2 + s3);
+            double piv = __shfl_sync(0xffffffffu, a[j], j);
+            if (!(piv > 0.0)) {
+                if (lane == j && blockIdx.x == 0) atomicOr(&flags[blockIdx.y], 1);
+                piv = 1.0;
             }
+            const double r = rsqrt(piv);
+            const double lij = (lane == j) ? piv * r : a[j] * r;
+            a[j] = lij;
+            if (lane == 0) invd[j] = r;
+            colj[lane] = lij;
             __syncwarp();
-            if (lane == j) {
-                if (!(sacc > 0.0)) {
-                    if (blockIdx.x == 0) atomicOr(&flags[blockIdx.y], 1);
-                    sacc = 1.0;
-                }
-                const double r = rsqrt(sacc);
-                invd[j] = r;
-                D[j][j] = sacc * r;
-            }
-            __syncwarp();
-            if (lane > j) D[lane][j] = sacc * invd[j];
+#pragma unroll
+            for (int k = j + 1; k < NB; ++k) a[k] -= lij * colj[k];
             __syncwarp();
         }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) D[lane][j] = (j <= lane) ? a[j] : 0.0;
     }
     __syncthreads();
     const int row = k0 + blockIdx.x * 128 + tid;

@@ -241,6 +241,15 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// (v0, v1) -> packed fp16 pair (round to nearest), and back
+__device__ __forceinline__ uint32_t pack_h2(float v0, float v1) {
+    const __half2 h = __floats2half2_rn(v0, v1);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&u);
+    return make_float2(__low2float(h), __high2float(h));
+}
 // x*s = hi + lo in fp32 (input differences of nearby fp64 coordinates must survive fp32)
 __device__ __forceinline__ void split_scaled(double x, double s, float& hi, float& lo) {
     const double v = x * s;

@@ -40,6 +40,12 @@ namespace {
 #ifndef HM_G2_CORR
 #define HM_G2_CORR 1      // diagonal lo x lo correction
 #endif
+#ifndef HM_G2_SYMDIAG
+#define HM_G2_SYMDIAG 1   // diagonal blocks: Y = Vh^T Vh + Vh^T (2 Vl), symmetrised by the reduce kernel (2 products instead of 3)
+#endif
+#ifndef HM_G2_CENTRE
+#define HM_G2_CENTRE 1    // level-1 windows start at minus half the expected window sum (truncation bias cancels)
+#endif
 constexpr int kC = HM_GRAM2_CHUNK;                 // data rows per chunk = MMA K extent per stage (4 x K16)
 constexpr int kStages = 3;
 constexpr int kHalf = 128 * 128;                   // 16 KB: 128 operand rows (inducing points) x 64 data rows fp16, SW128
@@ -59,7 +65,7 @@ constexpr int kThreads = (kGenWarps + 1 + kLoaders) * 32;
 constexpr uint32_t kAcc2 = 256;                    // TMEM column of the level-2 accumulator
 static_assert(kC == 64, "SWIZZLE_128B operand rows hold 64 fp16 values");
 
-struct Pending { double* slot; double inv_sc; uint32_t parity; bool to_l3, slot_fresh, acc2_fresh; };   // a deferred window fold
+struct Pending { double* slot; double inv_sc; uint32_t parity; int nfold; bool to_l3, slot_fresh; };   // a deferred window fold (nfold: windows already in level 2)
 struct Bars {
     uint64_t full[kStages], empty[kStages], rowfull[kRowSlots], rowempty[kRowSlots], accfull, accempty;
     uint32_t sflag[kStages];   // sign class of the chunk in the stage (for the MMA issuer)
@@ -159,6 +165,12 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
         Pending* pend = &sb->pend[warp];
         // fold one finished level-1 window (TMEM cols [0,256)) into level 2 (TMEM cols [256,512), fp32 round-to-nearest)
         // or, every f2 windows / at the end of a segment, level 1 + level 2 into the fp64 partial tile
+        // Centred accumulation.  tcgen05 accumulates with truncation: every MMA loses up to one ulp of the running sum
+        // TOWARDS ZERO, a bias that grows with the window length and that K_uu^-1 . K_uu^-1 amplifies.  The
+        // sums of a window all have one sign (V^T V with the sign of omega), so the accumulator of window w is started
+        // at I_w = -mean(previous window sums) / 2 instead of 0: it runs from -S/2 to +S/2 and the truncation bias of the
+        // two halves cancels.  I_w is a deterministic function of level 2 (which is read anyway), so the fold recomputes
+        // it instead of storing it.  The first window after every fp64 flush starts at 0.
         auto flush_window = [&]() {
             const Pending pd = *pend;
             mbar_wait_warp(&sb->accfull, pd.parity);
@@ -166,20 +178,31 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
             const int lq = warp & 3, wq = warp >> 2;
             const int i = lq * 32 + lane;
             const uint32_t tl = tmem_base + ((uint32_t)(lq * 32) << 16);
+            const float init_prev = HM_G2_CENTRE && pd.nfold > 0 ? -0.5f / (float)pd.nfold : 0.f;      // I_w = init_prev * L2_old
+            const float init_next = HM_G2_CENTRE ? -0.5f / (float)(pd.nfold + 1) : 0.f;                // I_{w+1} = init_next * L2_new
             for (int c16 = wq; c16 < 16; c16 += kGenWarps / 4) {   // units of 16 columns
                 uint32_t v[16];
                 tmem_ld16(tl + c16 * 16, v);
-                if (!pd.acc2_fresh) {
+                if (pd.nfold > 0) {
                     uint32_t u[16];
                     tmem_ld16(tl + kAcc2 + c16 * 16, u);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int p = 0; p < 16; ++p) v[p] = __float_as_uint(__uint_as_float(v[p]) + __uint_as_float(u[p]));
+                    for (int p = 0; p < 16; ++p) {
+                        const float l2 = __uint_as_float(u[p]);
+                        v[p] = __float_as_uint((__uint_as_float(v[p]) - init_prev * l2) + l2);   // level 2 += window sum
+                    }
                 } else {
                     tmem_ld_wait();
                 }
                 if (!pd.to_l3) {
                     tmem_st16(tl + kAcc2 + c16 * 16, v);
+                    if (HM_G2_CENTRE) {
+                        uint32_t w[16];
+#pragma unroll
+                        for (int p = 0; p < 16; ++p) w[p] = __float_as_uint(init_next * __uint_as_float(v[p]));
+                        tmem_st16(tl + c16 * 16, w);                                             // start value of the next window
+                    }
                 } else {
                     double2* dst = reinterpret_cast<double2*>(pd.slot + ((size_t)i * 256 + c16 * 16));
                     if (pd.slot_fresh) {
@@ -230,7 +253,7 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
             const double inv_k = cs->var[q];
             double* slot = slots + (size_t)(2 * sg.slot + (int)rank) * HM_GRAM_SLOT_DOUBLES;
             bool slot_fresh = true;    // level 3: first flush of the segment stores, later ones add
-            bool acc2_fresh = true;    // level 2: holds nothing yet
+            int nfold = 0;             // level 2: windows it holds
             int win = 0;
 
             for (int c0 = sg.chunk_begin; c0 < sg.chunk_end; c0 += f1, ++win) {
@@ -277,6 +300,13 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
                         for (int p = 0; p < 4; ++p) split2r(mul2(kv[p], sw[p]), hi[p], lo[p], res[p]);
                         if (diag) {
                             *reinterpret_cast<uint4*>(b_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            if (HM_G2_SYMDIAG) {
+                                // A diagonal block is symmetric: hh + hl + lh = sym(hh + 2 hl).  The lo operand is stored
+                                // doubled (exact) and only the two products A_hi.B_hi, A_hi.(2 B_lo) are issued; the reduce
+                                // kernel averages Y[i][j] and Y[j][i].
+#pragma unroll
+                                for (int p = 0; p < 4; ++p) lo[p] = pack_h2(2.f * res[p].x, 2.f * res[p].y);
+                            }
                             *reinterpret_cast<uint4*>(b_hi + kHalf + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                             // Ah.Bh + Ah.Bl + Al.Bh leaves out Al.Bl.  Between different inducing points the residuals are
                             // uncorrelated; on the diagonal entry both operands are the same value, the term is sgn . lo^2
@@ -304,7 +334,8 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
                                 }
                             }
                             *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0] ^ sgn.x, hi[1] ^ sgn.y, hi[2] ^ sgn.z, hi[3] ^ sgn.w);
-                            *reinterpret_cast<uint4*>(a_hi + kHalf + off) = make_uint4(lo[0] ^ sgn.x, lo[1] ^ sgn.y, lo[2] ^ sgn.z, lo[3] ^ sgn.w);
+                            if (!(HM_G2_SYMDIAG && diag))
+                                *reinterpret_cast<uint4*>(a_hi + kHalf + off) = make_uint4(lo[0] ^ sgn.x, lo[1] ^ sgn.y, lo[2] ^ sgn.z, lo[3] ^ sgn.w);
                         } else if (!diag || !HM_G2_ALIAS) {
                             *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                             *reinterpret_cast<uint4*>(a_hi + kHalf + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -334,11 +365,11 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
                 const bool to_l3 = ((win + 1) % f2 == 0) || (c1 == sg.chunk_end);
                 __syncwarp();
                 if (lane == 0) {
-                    pend->to_l3 = to_l3; pend->slot_fresh = slot_fresh; pend->acc2_fresh = acc2_fresh;
+                    pend->to_l3 = to_l3; pend->slot_fresh = slot_fresh; pend->nfold = nfold;
                     pend->slot = slot; pend->inv_sc = inv_sc; pend->parity = pend_parity;
                 }
                 __syncwarp();
-                if (to_l3) { slot_fresh = false; acc2_fresh = true; } else acc2_fresh = false;
+                if (to_l3) { slot_fresh = false; nfold = 0; } else ++nfold;
                 ++iv;
             }
             if (NV > 0 && sg.has_g) slot[(size_t)128 * 256 + rp * 128 + col] = g64 * inv_k;   // one partial per row part
@@ -353,8 +384,10 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
             for (int sgi = seg_begin; sgi < seg_end; ++sgi) {
                 const HmGramSeg sg = segs[sgi];
                 const bool diag = sg.j0 == sg.I * 256;
+                int nfold = 0;   // as in the generators: windows held by level 2 (then the fold pre-set the accumulator)
                 for (int c0 = sg.chunk_begin; c0 < sg.chunk_end; c0 += f1) {
                     const int c1 = min(sg.chunk_end, c0 + f1);
+                    const uint32_t preset = (HM_G2_CENTRE && nfold > 0) ? 1u : 0u;
                     mbar_wait_cluster(&sb->accempty, (iv & 1u) ^ 1u);
                     fence_after();
                     for (int c = c0; c < c1; ++c, ++cc_) {
@@ -373,15 +406,16 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
 #pragma unroll
                         for (int ks = 0; ks < kC / 16; ++ks) {
                             const uint64_t adv = (uint64_t)(ks * 2);   // 32 bytes per K=16 step, in 16-byte units
-                            mma2_f16(tmem_base, a_hi + adv, b_hi + adv, idc, (c > c0 || ks > 0) ? 1u : 0u);
+                            mma2_f16(tmem_base, a_hi + adv, b_hi + adv, idc, (c > c0 || ks > 0) ? 1u : preset);
                             if (npass >= 2) mma2_f16(tmem_base, a_hi + adv, b_lo + adv, idc, 1u);
-                            if (npass >= 3) mma2_f16(tmem_base, a_lo + adv, b_hi + adv, idc, 1u);
+                            if (npass >= 3 && !(HM_G2_SYMDIAG && diag)) mma2_f16(tmem_base, a_lo + adv, b_hi + adv, idc, 1u);
                             if (npass >= 4) mma2_f16(tmem_base, a_lo + adv, b_lo + adv, idc, 1u);   // diagnostic
                         }
                         commit2(&sb->empty[stage]);
                     }
                     commit2(&sb->accfull);
                     ++iv;
+                    nfold = (nfold + 1 == f2 || c1 == sg.chunk_end) ? 0 : nfold + 1;   // to_l3 of the generators
                 }
             }
         } else if (lane == 0) {
@@ -486,7 +520,8 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
 
 // Sum the partial tiles of every (q, block job) in slot order; write H (lower from the tile, mirrored) and g.
 __global__ void tc_gram2_reduce_kernel(const double* __restrict__ slots, const HmGramJob* __restrict__ jobs,
-                                       const int2* __restrict__ jobslots, int njobs, int nV, double* H, double* g0, int M, int Mp) {
+                                       const int2* __restrict__ jobslots, int njobs, int nV, double* H, double* g0, int M, int Mp,
+                                       int npass) {
     const int job = blockIdx.x >> 1, r = blockIdx.x & 1, q = blockIdx.y;
     const HmGramJob jb = jobs[job];
     const int2 sr = jobslots[q * njobs + job];
@@ -496,6 +531,14 @@ __global__ void tc_gram2_reduce_kernel(const double* __restrict__ slots, const H
         const int gr = row0 + i, gc = jb.j0 + j;
         if (gc > gr || gr >= M) continue;
         double s = 0.0;
+        if (HM_G2_SYMDIAG && jb.j0 == 256 * jb.I && npass >= 3) {
+            // symmetrise the diagonal block: H = (Y + Y^T) / 2; Y[lj][li] lives in the slot of CTA lj / 128
+            const int li = r * 128 + i, lj = j;
+            const int r2 = lj >> 7, i2 = lj & 127;
+            for (int sl = sr.x; sl < sr.y; ++sl)
+                s += 0.5 * (slots[(size_t)(2 * sl + r) * HM_GRAM_SLOT_DOUBLES + ((size_t)i * 256 + j)] +
+                            slots[(size_t)(2 * sl + r2) * HM_GRAM_SLOT_DOUBLES + ((size_t)i2 * 256 + li)]);
+        } else
         for (int sl = sr.x; sl < sr.y; ++sl) s += slots[(size_t)(2 * sl + r) * HM_GRAM_SLOT_DOUBLES + ((size_t)i * 256 + j)];
         if (gr == gc)   // the lo x lo term of the diagonal (see the generator)
             for (int sl = sr.x; sl < sr.y; ++sl)
@@ -567,9 +610,9 @@ int hm_tc_gram2(cudaStream_t s, const HmTasks& tk, const HmProjArgs& a, const Hm
 }
 
 int hm_tc_gram2_reduce(cudaStream_t s, const double* slots, const HmGramJob* jobs, const int2* jobslots, int njobs, int Q, int nV,
-                       double* H, double* g0, int M, int Mp) {
+                       double* H, double* g0, int M, int Mp, int npass) {
     dim3 grid((unsigned)(2 * njobs), (unsigned)Q, 16u);
-    tc_gram2_reduce_kernel<<<grid, 256, 0, s>>>(slots, jobs, jobslots, njobs, nV, H, g0, M, Mp);
+    tc_gram2_reduce_kernel<<<grid, 256, 0, s>>>(slots, jobs, jobslots, njobs, nV, H, g0, M, Mp, npass);
     HM_CUDA(cudaGetLastError());
     return 0;
 }
