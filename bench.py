@@ -16,8 +16,8 @@ the rows are sharded over the ranks and the packed sufficient statistics are sum
 
 value   steps/s with X, Y, the parameters, the gradients and the optimiser state resident in HBM.
 e2e     steps/s through the reference-facing call SVMOGPInf.inference(...) with HOST numpy buffers (pinned): every
-        step uploads X, Y and the parameters, downloads ELBO + gradients and applies the Adadelta update to the host
-        vector, all inside the timed region.  e2e_pageable: the same with ordinary (pageable) numpy arrays.
+        step uploads X, Y and the parameters and downloads ELBO + all gradients inside the timed region (evaluation
+        only, like the CPU arm).  e2e_pageable: the same with ordinary (pageable) numpy arrays.
 """
 import argparse
 import json
@@ -232,7 +232,6 @@ def main():
     from hetmogp_b200 import likelihoods as L
     from hetmogp_b200.het_likelihood import HetLikelihood
     from hetmogp_b200.gpy_shim import RBF, Coregionalize
-    from hetmogp_b200.optim import Adadelta
     lib, check = _lib.lib, _lib.check
 
     torch.cuda.set_device(local)
@@ -273,6 +272,11 @@ def main():
 
     # Optimiser over paramz' flat vector (svmogp.py:71-75 link order; kappa fixed as util.py:289 does, the lengthscale
     # free as in the VM steps of util.py:307): Adadelta state and both kernels on the device.
+    # climin's Adadelta with the reference's decay / momentum / offset.  The step rate is 1e-4 instead of util.py:324's
+    # 0.01: with full-batch gradients of N = 1e6 rows the first updates move every coordinate by 0.03 * step_rate, and at
+    # 0.01 the inducing inputs (spacing 2e-3) collide within the 25 steps of a driver run -- the benchmark would leave the
+    # configuration it is quoted on.  The kernels' work does not depend on the rate.
+    OPT_STEP_RATE = 1e-4
     opt = None
     n_opt = 0
     if not args.no_optimizer and what_id >= 1:
@@ -289,7 +293,7 @@ def main():
             arr[i].stride, arr[i].positive, arr[i].variational, arr[i].reserved = stride, pos, var, 0
             n_opt += n
         opt = C.c_void_p()
-        check(lib.hmogp_opt_create(local, arr, len(segs), 0.01, 0.9, 0.9, 1e-4, C.byref(opt)))
+        check(lib.hmogp_opt_create(local, arr, len(segs), OPT_STEP_RATE, 0.9, 0.9, 1e-4, C.byref(opt)))
         check(lib.hmogp_opt_gather(opt, C.c_void_p(stream)))
 
     def resident_step():
@@ -365,21 +369,16 @@ def main():
             inf = SVMOGPInf(precision=prec, device=local, group=group)
             inf._eng, inf._key = eng, (tuple(tuple(l.spec) for l in liks.likelihoods_list), M, Q, Xdim, prec, local)
             res = {}
-            nq = m_u.size + L_u.size
 
-            def fprime(w):       # the reference's stochastic_grad shape: parameters in, -gradient out, through inference()
-                m_u[...] = w[:m_u.size].reshape(m_u.shape)
-                L_u[...] = w[m_u.size:nq].reshape(L_u.shape)
+            def step():          # what svmogp.py:91-94 does per parameters_changed(): one inference() call on host arrays
                 lm, grads, _, _ = inf.inference(m_u, L_u, Xh, Yh, Z, kern_list, liks, B_list, meta, batch_scale=bscale, what=args.what)
                 res["lm"] = float(lm[0, 0])
-                if "dL_dmu_u" not in grads:
-                    return np.zeros_like(w)
-                return -np.concatenate([np.hstack(grads["dL_dmu_u"]).ravel(), np.hstack(grads["dL_dL_u"]).ravel()])
-            it = iter(Adadelta(np.concatenate([m_u.ravel(), L_u.ravel()]), fprime, step_rate=0.01, momentum=0.9))
-            ms, _, _ = timed(lambda: next(it), args.steps, 3)
+            ms, _, _ = timed(step, args.steps, 3)
             return {"value": 1e3 / ms, "unit": "ELBO steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms, "elbo": res.get("lm"), "host_buffers": "pinned" if pinned else "pageable",
-                    "optimizer": "Adadelta update of q(U) on the host vector inside the timed region"}
+                    "scope": "SVMOGPInf.inference(...) round trip: upload of X, Y and the parameters, evaluation, download of ELBO and "
+                             "all gradients; no optimiser update (the reference keeps the flat vector in paramz / climin on the host, "
+                             "as does the CPU arm this number is compared with)"}
         e2e = e2e_arm(True)
         e2e_pageable = e2e_arm(False)
 
@@ -472,7 +471,7 @@ def main():
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": {"tc": "f16x2 split (fp16 hi/lo on tcgen05, fp32 accumulate; fp64 M x M algebra)", "fp32": "f32", "fp64": "f64"}[prec],
             "data": "synthetic", "config": workload_config(args, c), "elbo": elbo_resident, "clocks": clocks,
-            "gpu_launches": launches, "optimizer": None if opt is None else {"kind": "Adadelta (climin semantics), device-resident", "flat_size": n_opt},
+            "gpu_launches": launches, "optimizer": None if opt is None else {"kind": "Adadelta (climin semantics), device-resident", "flat_size": n_opt, "step_rate": OPT_STEP_RATE},
             "e2e": e2e, "e2e_pageable": e2e_pageable, "variants": variants, "parity": parity,
             "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": wall}
     print(json.dumps(line))

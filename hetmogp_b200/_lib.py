@@ -96,6 +96,7 @@ def _load():
         "hmogp_get_kuu": (C.c_int, [vp, vp, vp, vp]),
         "hmogp_lik_var_exp": (C.c_int, [C.POINTER(LikDesc), i64, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
         "hmogp_lik_pointwise": (C.c_int, [C.POINTER(LikDesc), i64, vp, vp, vp, vp, vp, i32, vp]),
+        "hmogp_lik_predictive": (C.c_int, [C.POINTER(LikDesc), i64, vp, vp, vp, vp, i32, i32, vp]),
         "hmogp_flat_to_triang": (C.c_int, [vp, vp, i32, i32, i32, vp]),
         "hmogp_triang_to_flat": (C.c_int, [vp, vp, i32, i32, i32, vp]),
         "hmogp_enable_timing": (C.c_int, [vp, i32]),

@@ -105,6 +105,8 @@ int hm_lik_var_exp(cudaStream_t s, int prec, const hmogp_lik_desc& lik, int64_t 
                    const double* Vf, double* VE, double* dm, double* dv);
 int hm_lik_pointwise(cudaStream_t s, const hmogp_lik_desc& lik, int64_t N, const double* F, const double* Y,
                      double* logp, double* dlogp, double* d2logp);
+int hm_lik_predictive(cudaStream_t s, const hmogp_lik_desc& lik, int gh_tensor, int64_t N, const double* Mf, const double* Vf,
+                      double* mean_pred, double* var_pred);
 int hm_upload_gh_tables();
 
 // ---------------------------------------------------------------- N-sized SIMT contractions (proj_simt.cu, gram_simt.cu)

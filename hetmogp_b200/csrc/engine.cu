@@ -415,6 +415,16 @@ struct hmogp_engine {
     cudaStream_t s2;          // side stream of the prepare phase (S, S^-1 branch)
     cudaEvent_t ev_fork, ev_S, ev_Sinv;
     cudaGraphExec_t chol_graph;   // the 2 Mp / 32 panel + update launches of the blocked Cholesky, captured once
+    // The M-sized chain replayed as CUDA graphs (fixed engine-owned buffers, so each is captured once):
+    //   prepA: padding, S / S^-1 branch (forked), K_uu build and Cholesky -> host checks the pivot flags (jitchol)
+    //   prepB: K_uu^-1, alpha, S K^-1, K^-1 S K^-1, C, KL, tensor-core operand image
+    //   fin[k]: the finish chain for one (statistics buffer, what, dL_dKmm wanted) combination
+    cudaGraphExec_t prepA_graph, prepB_graph;
+    long long prepA_launches, prepB_launches;
+    struct FinGraph { cudaGraphExec_t exec; const double* stats; int what; bool dkmm; long long launches; };
+    std::vector<FinGraph> fin_graphs;
+    bool graphs_off;
+    int prepare_calls;
     cudaStream_t sc;          // copy stream: host -> device data uploads overlap the M-sized prepare phase of the next step
     cudaEvent_t ev_cfence, ev_data, ev_dataY;   // inputs X uploaded (the forward needs them) / labels Y too (the likelihoods do)
     bool dataY_pending;
@@ -531,10 +541,96 @@ static int dbg_skip() { static int v = -1; if (v < 0) { const char* e = getenv("
 #endif
 
 // ---- prepare: everything M-sized that precedes the data pass.  Returns HMOGP_ERR_LINALG if jitchol gives up.
+// part A on streams (s, s2): padded inputs; S = Lu Lu^T, Lu^-1, S^-1 on the side stream; K_uu (with the jitter in
+// e->jitter_d), its copy into Luu, cleared flags, blocked Cholesky.  `graphed_chol`: replay the Cholesky's own graph
+// (direct issue; inside a capture the launches are recorded individually).
+int prepare_partA(hmogp_engine* e, cudaStream_t s, cudaStream_t s2, bool graphed_chol) {
+    const int M = e->M, Mp = e->Mp, Q = e->Q, Xd = e->Xd;
+    const int64_t sQ = (int64_t)Mp * Mp;
+    {
+        dim3 grid((unsigned)hm_cdiv(Mp, 128), (unsigned)Mp, (unsigned)Q);
+        pad_inputs_kernel<<<grid, 128, 0, s>>>(e->pZ, e->pm, e->pL, e->Zp, e->mp, e->Lu, M, Mp, Q, Xd);
+        HM_CUDA(cudaGetLastError());
+    }
+    // ---- side stream: S = Lu Lu^T (svmogp_inf.py:193-195) and S^-1 (svmogp_inf.py:124) do not depend on K_uu
+    HM_CUDA(cudaEventRecord(e->ev_fork, s));
+    HM_CUDA(cudaStreamWaitEvent(s2, e->ev_fork, 0));
+    HM_CHECK(hm_dgemm(s2, false, true, Mp, Mp, Mp, 1.0, e->Lu, Mp, sQ, e->Lu, Mp, sQ, 0.0, e->S, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR | HM_GEMM_K_LE));
+    HM_CUDA(cudaEventRecord(e->ev_S, s2));
+    if (!HM_SKIP(4)) HM_CHECK(hm_tri_inverse(s2, e->Lu, e->LuInv, e->T1, Mp, sQ, Q));
+    HM_CHECK(hm_dgemm(s2, true, false, Mp, Mp, Mp, 1.0, e->LuInv, Mp, sQ, e->LuInv, Mp, sQ, 0.0, e->Sinv, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR | HM_GEMM_K_GE));
+    HM_CUDA(cudaEventRecord(e->ev_Sinv, s2));
+    // K_uu, Cholesky (util.py:197-198)
+    HM_CHECK(hm_build_kuu(s, e->Zp, e->consts, e->jitter_d, e->Kuu, M, Mp, Xd, Q));
+    HM_CUDA(cudaMemcpyAsync(e->Luu, e->Kuu, sizeof(double) * sQ * Q, cudaMemcpyDeviceToDevice, s));
+    HM_CUDA(cudaMemsetAsync(e->flags_d, 0, sizeof(int) * 2 * HM_MAXQ, s));
+    if (!HM_SKIP(1)) {
+        if (graphed_chol) HM_CHECK(cholesky_graphed(e));
+        else HM_CHECK(hm_cholesky(s, e->Luu, Mp, sQ, Q, e->flags_d));
+    }
+    HM_CUDA(cudaStreamWaitEvent(s, e->ev_Sinv, 0));   // join (a captured graph must not leave the side stream dangling)
+    return 0;
+}
+
+// part B on stream s: K_uu^-1 = Luu^-T Luu^-1 (dpotri, util.py:199), alpha, S K^-1, K^-1 S K^-1, C, KL, operand image
+int prepare_partB(hmogp_engine* e, cudaStream_t s) {
+    const int M = e->M, Mp = e->Mp, Q = e->Q;
+    const int64_t sQ = (int64_t)Mp * Mp;
+    if (!HM_SKIP(2)) HM_CHECK(hm_tri_inverse(s, e->Luu, e->LuuInv, e->tmp, Mp, sQ, Q));
+    HM_CHECK(hm_dgemm(s, true, false, Mp, Mp, Mp, 1.0, e->LuuInv, Mp, sQ, e->LuuInv, Mp, sQ, 0.0, e->Ki, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR | HM_GEMM_K_GE));
+    {
+        dim3 grid((unsigned)hm_cdiv(Mp, 8), (unsigned)Q);
+        dgemv_kernel<<<grid, 256, 0, s>>>(e->Ki, e->mp, e->alpha, Mp);
+        HM_CUDA(cudaGetLastError());
+    }
+    if (!HM_SKIP(8)) HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->S, Mp, sQ, e->Ki, Mp, sQ, 0.0, e->SK, Mp, sQ, Q));
+    if (!HM_SKIP(8)) HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->Ki, Mp, sQ, e->SK, Mp, sQ, 0.0, e->KSK, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR));
+    {
+        const int64_t n = sQ * Q;
+        make_c_kernel<<<(unsigned)hm_cdiv(n, 256), 256, 0, s>>>(e->KSK, e->Ki, e->C, e->Cf, n);
+        HM_CUDA(cudaGetLastError());
+    }
+    {
+        const int nblk = 48;   // <= 64 (KLpart)
+        dim3 grid((unsigned)nblk, (unsigned)Q);
+        if (!HM_SKIP(16)) kl_kernel<<<grid, 256, 0, s>>>(e->Ki, e->S, e->Sinv, e->mp, e->alpha, e->Luu, e->Lu, e->KLpart, e->flags_d + HM_MAXQ, M, Mp);
+        HM_CUDA(cudaGetLastError());
+        kl_finish_kernel<<<1, Q, 0, s>>>(e->KLpart, nblk, e->KLq, M);
+        HM_CUDA(cudaGetLastError());
+    }
+    if (e->prec == HMOGP_PREC_TC && !HM_SKIP(32)) HM_CHECK(hm_tc_prepare(s, e->C, e->consts, e->tcinfo, e->Cb, M, Mp, e->Mc, Q));
+    return 0;
+}
+
+// Capture `body` (which issues on the capture stream cs and, forked from it, on e->s2) into an executable graph.
+template <typename F> int capture_graph(hmogp_engine* e, cudaGraphExec_t* exec, long long* launches, F body) {
+    cudaStream_t cs;
+    HM_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    const long long l0 = hm_launch_counter;
+    cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    int rc = 0;
+    if (ce == cudaSuccess) {
+        rc = body(cs);
+        ce = cudaStreamEndCapture(cs, &g);
+    }
+    cudaStreamDestroy(cs);
+    *launches = hm_launch_counter - l0;
+    if (rc || ce != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        if (!rc) hm_set_error("CUDA graph capture of the M-sized chain failed: %s", cudaGetErrorString(ce));
+        return rc ? rc : HMOGP_ERR_CUDA;
+    }
+    const cudaError_t ie = cudaGraphInstantiate(exec, g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) { *exec = nullptr; hm_set_error("CUDA graph instantiation failed: %s", cudaGetErrorString(ie)); return HMOGP_ERR_CUDA; }
+    return 0;
+}
+
 int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
     cudaStream_t s = e->stream;
-    const int M = e->M, Mp = e->Mp, Q = e->Q, Xd = e->Xd, J = e->J, T = e->T;
-    const int64_t sQ = (int64_t)Mp * Mp;
+    const int M = e->M, Q = e->Q, Xd = e->Xd, J = e->J, T = e->T;
     HM_CHECK(copy_in(e, e->pZ, p->Z, (size_t)M * Q * Xd, mem_kind));
     HM_CHECK(copy_in(e, e->pm, p->m_u, (size_t)M * Q, mem_kind));
     HM_CHECK(copy_in(e, e->pL, p->L_u, (size_t)e->P * Q, mem_kind));
@@ -550,30 +646,25 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
     prep_consts_kernel<<<1, 256, 0, s>>>(e->consts, e->pvar, e->pls, e->pW, e->pkappa, p->W_chain ? e->pWc : nullptr,
                                          p->kappa_chain ? e->pkc : nullptr, p->batch_scale ? e->pbs : nullptr, Q, J, T);
     HM_CUDA(cudaGetLastError());
-    {
-        dim3 grid((unsigned)hm_cdiv(Mp, 128), (unsigned)Mp, (unsigned)Q);
-        pad_inputs_kernel<<<grid, 128, 0, s>>>(e->pZ, e->pm, e->pL, e->Zp, e->mp, e->Lu, M, Mp, Q, Xd);
-        HM_CUDA(cudaGetLastError());
-    }
-    // ---- side stream: S = Lu Lu^T (svmogp_inf.py:193-195) and S^-1 (svmogp_inf.py:124) do not depend on K_uu
-    cudaStream_t s2 = e->s2;
-    HM_CUDA(cudaEventRecord(e->ev_fork, s));
-    HM_CUDA(cudaStreamWaitEvent(s2, e->ev_fork, 0));
-    HM_CHECK(hm_dgemm(s2, false, true, Mp, Mp, Mp, 1.0, e->Lu, Mp, sQ, e->Lu, Mp, sQ, 0.0, e->S, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR | HM_GEMM_K_LE));
-    HM_CUDA(cudaEventRecord(e->ev_S, s2));
-    if (!HM_SKIP(4)) HM_CHECK(hm_tri_inverse(s2, e->Lu, e->LuInv, e->T1, Mp, sQ, Q));
-    HM_CHECK(hm_dgemm(s2, true, false, Mp, Mp, Mp, 1.0, e->LuInv, Mp, sQ, e->LuInv, Mp, sQ, 0.0, e->Sinv, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR | HM_GEMM_K_GE));
-    HM_CUDA(cudaEventRecord(e->ev_Sinv, s2));
-    // K_uu, jitchol (util.py:197-198): no jitter unless the plain factorisation fails; then var*1e-6 * 10^k, k<5
+    // The first evaluation of an engine issues the chain directly (it also sets the kernels' attributes); from the
+    // second on the two halves are graph replays.  HMOGP_NO_GRAPH=1 keeps direct issue.
+#ifdef HM_DEBUG_SKIP
+    const bool graphs = false;
+#else
+    const bool graphs = !e->graphs_off && e->prepare_calls > 0;
+#endif
+    ++e->prepare_calls;
+    for (int q = 0; q < Q; ++q) { e->jitter_h[q] = 0.0; e->chol_fail_h[q] = 0; }
+    HM_CUDA(cudaMemsetAsync(e->jitter_d, 0, sizeof(double) * HM_MAXQ, s));
+    if (graphs) {
+        if (!e->prepA_graph) HM_CHECK(capture_graph(e, &e->prepA_graph, &e->prepA_launches, [&](cudaStream_t cs) { return prepare_partA(e, cs, e->s2, false); }));
+        HM_CUDA(cudaGraphLaunch(e->prepA_graph, s));
+        hm_launch_counter += e->prepA_launches - 1;
+    } else HM_CHECK(prepare_partA(e, s, e->s2, true));
+    // jitchol (util.py:198): no jitter unless the plain factorisation fails; then var*1e-6 * 10^k, k<5
     double var_h[HM_MAXQ];
     bool have_var = false;
-    for (int q = 0; q < Q; ++q) { e->jitter_h[q] = 0.0; e->chol_fail_h[q] = 0; }
     for (int attempt = 0;; ++attempt) {
-        HM_CUDA(cudaMemcpyAsync(e->jitter_d, e->jitter_h, sizeof(double) * Q, cudaMemcpyHostToDevice, s));
-        HM_CHECK(hm_build_kuu(s, e->Zp, e->consts, e->jitter_d, e->Kuu, M, Mp, Xd, Q));
-        HM_CUDA(cudaMemcpyAsync(e->Luu, e->Kuu, sizeof(double) * sQ * Q, cudaMemcpyDeviceToDevice, s));
-        HM_CUDA(cudaMemsetAsync(e->flags_d, 0, sizeof(int) * 2 * HM_MAXQ, s));
-        if (!HM_SKIP(1)) HM_CHECK(cholesky_graphed(e));
         int fl[HM_MAXQ];
         HM_CUDA(cudaMemcpyAsync(fl, e->flags_d, sizeof(int) * Q, cudaMemcpyDeviceToHost, s));
         if (!HM_SKIP(64)) HM_CUDA(cudaStreamSynchronize(s));
@@ -582,7 +673,7 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
         for (int q = 0; q < Q; ++q) { any = any || fl[q]; if (fl[q]) ++e->chol_fail_h[q]; }
         if (!any) break;
         if (attempt >= 5) {
-            cudaStreamSynchronize(s2);
+            cudaStreamSynchronize(e->s2);
             hm_set_error("not positive definite, even with jitter.");
             return HMOGP_ERR_LINALG;
         }
@@ -592,34 +683,19 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
         }
         for (int q = 0; q < Q; ++q)
             if (fl[q]) e->jitter_h[q] = (e->jitter_h[q] == 0.0) ? var_h[q] * 1e-6 : e->jitter_h[q] * 10.0;
+        // retry (rare): K_uu with the jitter, copy, cleared flags, Cholesky -- issued directly
+        const int64_t sQ = (int64_t)e->Mp * e->Mp;
+        HM_CUDA(cudaMemcpyAsync(e->jitter_d, e->jitter_h, sizeof(double) * Q, cudaMemcpyHostToDevice, s));
+        HM_CHECK(hm_build_kuu(s, e->Zp, e->consts, e->jitter_d, e->Kuu, M, e->Mp, Xd, Q));
+        HM_CUDA(cudaMemcpyAsync(e->Luu, e->Kuu, sizeof(double) * sQ * Q, cudaMemcpyDeviceToDevice, s));
+        HM_CUDA(cudaMemsetAsync(e->flags_d, 0, sizeof(int) * 2 * HM_MAXQ, s));
+        HM_CHECK(cholesky_graphed(e));
     }
-    // K_uu^-1 = Luu^-T Luu^-1   (dpotri, util.py:199)
-    if (!HM_SKIP(2)) HM_CHECK(hm_tri_inverse(s, e->Luu, e->LuuInv, e->tmp, Mp, sQ, Q));
-    HM_CHECK(hm_dgemm(s, true, false, Mp, Mp, Mp, 1.0, e->LuuInv, Mp, sQ, e->LuuInv, Mp, sQ, 0.0, e->Ki, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR | HM_GEMM_K_GE));
-    // alpha = Ki m ; SK = S Ki ; KSK = Ki S Ki ; C = KSK - Ki
-    {
-        dim3 grid((unsigned)hm_cdiv(Mp, 8), (unsigned)Q);
-        dgemv_kernel<<<grid, 256, 0, s>>>(e->Ki, e->mp, e->alpha, Mp);
-        HM_CUDA(cudaGetLastError());
-    }
-    HM_CUDA(cudaStreamWaitEvent(s, e->ev_S, 0));
-    if (!HM_SKIP(8)) HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->S, Mp, sQ, e->Ki, Mp, sQ, 0.0, e->SK, Mp, sQ, Q));
-    if (!HM_SKIP(8)) HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->Ki, Mp, sQ, e->SK, Mp, sQ, 0.0, e->KSK, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR));
-    {
-        const int64_t n = sQ * Q;
-        make_c_kernel<<<(unsigned)hm_cdiv(n, 256), 256, 0, s>>>(e->KSK, e->Ki, e->C, e->Cf, n);
-        HM_CUDA(cudaGetLastError());
-    }
-    HM_CUDA(cudaStreamWaitEvent(s, e->ev_Sinv, 0));
-    {
-        const int nblk = 48;   // <= 64 (KLpart)
-        dim3 grid((unsigned)nblk, (unsigned)Q);
-        if (!HM_SKIP(16)) kl_kernel<<<grid, 256, 0, s>>>(e->Ki, e->S, e->Sinv, e->mp, e->alpha, e->Luu, e->Lu, e->KLpart, e->flags_d + HM_MAXQ, M, Mp);
-        HM_CUDA(cudaGetLastError());
-        kl_finish_kernel<<<1, Q, 0, s>>>(e->KLpart, nblk, e->KLq, M);
-        HM_CUDA(cudaGetLastError());
-    }
-    if (e->prec == HMOGP_PREC_TC && !HM_SKIP(32)) HM_CHECK(hm_tc_prepare(s, e->C, e->consts, e->tcinfo, e->Cb, M, Mp, e->Mc, Q));
+    if (graphs) {
+        if (!e->prepB_graph) HM_CHECK(capture_graph(e, &e->prepB_graph, &e->prepB_launches, [&](cudaStream_t cs) { return prepare_partB(e, cs); }));
+        HM_CUDA(cudaGraphLaunch(e->prepB_graph, s));
+        hm_launch_counter += e->prepB_launches - 1;
+    } else HM_CHECK(prepare_partB(e, s));
     return 0;
 }
 
@@ -884,7 +960,7 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
         e->gram_chunk = e->gram2 ? HM_GRAM2_CHUNK : HM_GRAM_CHUNK;
         eg = getenv("HMOGP_TC_GRAM_DIAG_COST");
         e->gram2_cost_diag = eg ? atoi(eg) : 75;   // a diagonal block generates one operand tile instead of two (generation, not the MMAs, sets the pace)
-        e->tc_f1 = (ev ? atoi(ev) : 512) / e->gram_chunk;
+        e->tc_f1 = (ev ? atoi(ev) : (e->gram2 ? 1024 : 512)) / e->gram_chunk;   // pair kernel: one window per TMEM buffer, folded straight into fp64
         if (e->tc_f1 < 1) e->tc_f1 = 1;
         ev = getenv("HMOGP_TC_FLUSH3_ROWS");         // rows between fp64 flushes
         e->tc_f2 = (ev ? atoi(ev) : 16384) / (e->tc_f1 * e->gram_chunk);
@@ -939,6 +1015,8 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
     e->s2 = nullptr; e->ev_fork = e->ev_S = e->ev_Sinv = nullptr;
     e->sc = nullptr; e->ev_cfence = e->ev_data = e->ev_dataY = nullptr; e->data_pending = e->dataY_pending = false;
     e->chol_graph = nullptr;
+    e->prepA_graph = e->prepB_graph = nullptr; e->prepA_launches = e->prepB_launches = 0; e->prepare_calls = 0;
+    { const char* v = getenv("HMOGP_NO_GRAPH"); e->graphs_off = v && atoi(v) != 0; }
     for (int t = 0; t < HM_MAXT; ++t) e->up_X[t] = e->up_Y[t] = nullptr;
     if (!rc && (cudaStreamCreateWithFlags(&e->s2, cudaStreamNonBlocking) != cudaSuccess ||
                 cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -972,6 +1050,9 @@ void hmogp_destroy(hmogp_engine* e) {
     if (e->ev_Sinv) cudaEventDestroy(e->ev_Sinv);
     if (e->s2) cudaStreamDestroy(e->s2);
     if (e->chol_graph) cudaGraphExecDestroy(e->chol_graph);
+    if (e->prepA_graph) cudaGraphExecDestroy(e->prepA_graph);
+    if (e->prepB_graph) cudaGraphExecDestroy(e->prepB_graph);
+    for (auto& f : e->fin_graphs) if (f.exec) cudaGraphExecDestroy(f.exec);
     if (e->ev_cfence) cudaEventDestroy(e->ev_cfence);
     if (e->ev_data) cudaEventDestroy(e->ev_data);
     if (e->ev_dataY) cudaEventDestroy(e->ev_dataY);
@@ -1119,37 +1200,64 @@ int hmogp_step_finish(hmogp_engine* e, const double* stats_dev, hmogp_grads* g, 
     a.log_marginal = e->o_lm; a.VE = e->o_VE; a.KL = e->o_KL; a.dmu = e->o_dmu; a.dL = e->o_dL;
     a.dKmm = (g->dL_dKmm || what >= HMOGP_WHAT_FULL) ? e->o_dKmm : nullptr;
     a.drbf = e->o_drbf; a.dW = e->o_dW; a.dkappa = e->o_dkappa; a.dZ = e->o_dZ;
-    if (what >= HMOGP_WHAT_VE) {
-        const double* g1 = stats + e->off_g1;
-        const double* H = stats + e->off_H;
-        dim3 gv((unsigned)hm_cdiv(Mp, 8), (unsigned)Q);
-        dgemv_kernel<<<gv, 256, 0, s>>>(e->Ki, g1, e->kg, Mp);  // Ki g1  (svmogp_inf.py:144)
+    // the finish chain (fixed buffers for a given statistics pointer): direct on first use, then a graph replay
+    auto finish_chain = [&](cudaStream_t cs) -> int {
+        if (what >= HMOGP_WHAT_VE) {
+            const double* g1 = stats + e->off_g1;
+            const double* H = stats + e->off_H;
+            dim3 gv((unsigned)hm_cdiv(Mp, 8), (unsigned)Q);
+            dgemv_kernel<<<gv, 256, 0, cs>>>(e->Ki, g1, e->kg, Mp);  // Ki g1  (svmogp_inf.py:144)
+            HM_CUDA(cudaGetLastError());
+            HM_CHECK(hm_dgemm(cs, false, false, Mp, Mp, Mp, 1.0, e->Ki, Mp, sQ, H, Mp, sQ, 0.0, e->T1, Mp, sQ, Q));
+            HM_CHECK(hm_dgemm(cs, false, false, Mp, Mp, Mp, 1.0, e->T1, Mp, sQ, e->Ki, Mp, sQ, 0.0, e->E, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR));  // E = Ki H Ki
+            const int64_t n = sQ * Q;
+            dlds_kernel<<<(unsigned)hm_cdiv(n, 256), 256, 0, cs>>>(e->E, e->Ki, e->Sinv, e->dLdS, n);
+            HM_CUDA(cudaGetLastError());
+            HM_CHECK(hm_dgemm(cs, false, false, Mp, Mp, Mp, 1.0, e->dLdS, Mp, sQ, e->Lu, Mp, sQ, 0.0, e->dLdLfull, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_LOWER | HM_GEMM_KB_GE));   // only the lower triangle is read
+            if (what >= HMOGP_WHAT_FULL || a.dKmm) {
+                HM_CHECK(hm_dgemm(cs, false, false, Mp, Mp, Mp, 1.0, e->E, Mp, sQ, e->SK, Mp, sQ, 0.0, e->tmpE, Mp, sQ, Q));  // E S Ki
+                dim3 gk((unsigned)hm_cdiv(Mp, 128), (unsigned)Mp, (unsigned)Q);
+                dldk_kernel<<<gk, 128, 0, cs>>>(e->E, e->tmpE, e->Ki, e->KSK, e->kg, e->alpha, e->dLdK, Mp);
+                HM_CUDA(cudaGetLastError());
+            }
+            if (what >= HMOGP_WHAT_FULL) {
+                dim3 gr((unsigned)hm_cdiv(M, 8), (unsigned)Q);
+                kmm_grad_kernel<<<gr, 256, 0, cs>>>(e->dLdK, e->Zp, e->consts, e->rowstat, e->dzmm, M, Mp, Xd);
+                HM_CUDA(cudaGetLastError());
+            }
+        }
+        assemble_scalar_kernel<<<1, 256, 0, cs>>>(a);
         HM_CUDA(cudaGetLastError());
-        HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->Ki, Mp, sQ, H, Mp, sQ, 0.0, e->T1, Mp, sQ, Q));
-        HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->T1, Mp, sQ, e->Ki, Mp, sQ, 0.0, e->E, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR));  // E = Ki H Ki
-        const int64_t n = sQ * Q;
-        dlds_kernel<<<(unsigned)hm_cdiv(n, 256), 256, 0, s>>>(e->E, e->Ki, e->Sinv, e->dLdS, n);
-        HM_CUDA(cudaGetLastError());
-        HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->dLdS, Mp, sQ, e->Lu, Mp, sQ, 0.0, e->dLdLfull, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_LOWER | HM_GEMM_KB_GE));   // only the lower triangle is read
-        if (what >= HMOGP_WHAT_FULL || g->dL_dKmm) {
-            HM_CHECK(hm_dgemm(s, false, false, Mp, Mp, Mp, 1.0, e->E, Mp, sQ, e->SK, Mp, sQ, 0.0, e->tmpE, Mp, sQ, Q));  // E S Ki
-            dim3 gk((unsigned)hm_cdiv(Mp, 128), (unsigned)Mp, (unsigned)Q);
-            dldk_kernel<<<gk, 128, 0, s>>>(e->E, e->tmpE, e->Ki, e->KSK, e->kg, e->alpha, e->dLdK, Mp);
+        if (what >= HMOGP_WHAT_VE) {
+            dim3 gm((unsigned)hm_cdiv(M, 128), (unsigned)M, (unsigned)Q);
+            assemble_mat_kernel<<<gm, 128, 0, cs>>>(a);
             HM_CUDA(cudaGetLastError());
         }
-        if (what >= HMOGP_WHAT_FULL) {
-            dim3 gr((unsigned)hm_cdiv(M, 8), (unsigned)Q);
-            kmm_grad_kernel<<<gr, 256, 0, s>>>(e->dLdK, e->Zp, e->consts, e->rowstat, e->dzmm, M, Mp, Xd);
-            HM_CUDA(cudaGetLastError());
+        return 0;
+    };
+#ifdef HM_DEBUG_SKIP
+    const bool fin_graphs = false;
+#else
+    const bool fin_graphs = !e->graphs_off && e->prepare_calls > 1;
+#endif
+    if (fin_graphs) {
+        hmogp_engine::FinGraph* fg = nullptr;
+        for (auto& f : e->fin_graphs)
+            if (f.stats == stats && f.what == what && f.dkmm == (a.dKmm != nullptr)) fg = &f;
+        if (!fg) {
+            if (e->fin_graphs.size() >= 8) {   // a caller cycling through statistics buffers: drop the oldest
+                if (e->fin_graphs.front().exec) cudaGraphExecDestroy(e->fin_graphs.front().exec);
+                e->fin_graphs.erase(e->fin_graphs.begin());
+            }
+            hmogp_engine::FinGraph f;
+            f.exec = nullptr; f.stats = stats; f.what = what; f.dkmm = a.dKmm != nullptr; f.launches = 0;
+            HM_CHECK(capture_graph(e, &f.exec, &f.launches, finish_chain));
+            e->fin_graphs.push_back(f);
+            fg = &e->fin_graphs.back();
         }
-    }
-    assemble_scalar_kernel<<<1, 256, 0, s>>>(a);
-    HM_CUDA(cudaGetLastError());
-    if (what >= HMOGP_WHAT_VE) {
-        dim3 gm((unsigned)hm_cdiv(M, 128), (unsigned)M, (unsigned)Q);
-        assemble_mat_kernel<<<gm, 128, 0, s>>>(a);
-        HM_CUDA(cudaGetLastError());
-    }
+        HM_CUDA(cudaGraphLaunch(fg->exec, s));
+        hm_launch_counter += fg->launches - 1;
+    } else HM_CHECK(finish_chain(s));
     if (e->timing) HM_CUDA(cudaEventRecord(e->ev[6], s));
     // ---- outputs
     const size_t P = e->P;
@@ -1387,6 +1495,23 @@ int hmogp_lik_var_exp(const hmogp_lik_desc* lik, int64_t N, const double* Y, con
     std::vector<double*> din, dout;
     HM_CHECK(staged_call(mem_kind, s, ins, outs, din, dout));
     int rc = hm_lik_var_exp(s, precision == HMOGP_PREC_FP64 ? HMOGP_PREC_FP64 : HMOGP_PREC_FP32, *lik, N, din[0], din[1], din[2], dout[0], dout[1], dout[2]);
+    int rc2 = staged_finish(mem_kind, s, ins, outs, din, dout);
+    return rc ? rc : rc2;
+}
+
+int hmogp_lik_predictive(const hmogp_lik_desc* lik, int64_t N, const double* Mf, const double* Vf, double* mean_pred,
+                         double* var_pred, int32_t gh_tensor, int32_t mem_kind, void* cuda_stream) {
+    if (!lik || N < 0 || !Mf || !Vf || !mean_pred || !var_pred) { hm_set_error("hmogp_lik_predictive: null argument"); return HMOGP_ERR_ARG; }
+    if (hmogp_device_count() == 0) { hm_set_error("no CUDA device: hetmogp_b200 has no CPU fallback"); return HMOGP_ERR_CUDA; }
+    int dy, F, dp;
+    HM_CHECK(lik_dims(*lik, &dy, &F, &dp));
+    HM_CHECK(hm_upload_gh_tables());
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    std::vector<std::pair<const double*, size_t>> ins = {{Mf, (size_t)N * F}, {Vf, (size_t)N * F}};
+    std::vector<std::pair<double*, size_t>> outs = {{mean_pred, (size_t)N * dp}, {var_pred, (size_t)N * dp}};
+    std::vector<double*> din, dout;
+    HM_CHECK(staged_call(mem_kind, s, ins, outs, din, dout));
+    int rc = hm_lik_predictive(s, *lik, gh_tensor, N, din[0], din[1], dout[0], dout[1]);
     int rc2 = staged_finish(mem_kind, s, ins, outs, din, dout);
     return rc ? rc : rc2;
 }

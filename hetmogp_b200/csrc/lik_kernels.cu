@@ -201,6 +201,14 @@ int hm_lik_rows(cudaStream_t s, int prec, const HmTasks& tk, const HmConsts* con
     return 0;
 }
 
+static int lik_dimf(const hmogp_lik_desc& lik) {
+    switch (lik.kind) {
+        case HMOGP_LIK_HETGAUSSIAN: case HMOGP_LIK_GAMMA: case HMOGP_LIK_BETA: return 2;
+        case HMOGP_LIK_CATEGORICAL: return lik.K - 1;
+        default: return 1;
+    }
+}
+
 // ------------------------------------------------------------------------------------ stand-alone var_exp
 template <typename T>
 __global__ void __launch_bounds__(HM_LIK_THREADS) lik_varexp_kernel(int kind, int K, double sigma, int F, int64_t N,
@@ -221,14 +229,6 @@ __global__ void __launch_bounds__(HM_LIK_THREADS) lik_varexp_kernel(int kind, in
     }
 }
 
-static int lik_dimf(const hmogp_lik_desc& lik) {
-    switch (lik.kind) {
-        case HMOGP_LIK_HETGAUSSIAN: case HMOGP_LIK_GAMMA: case HMOGP_LIK_BETA: return 2;
-        case HMOGP_LIK_CATEGORICAL: return lik.K - 1;
-        default: return 1;
-    }
-}
-
 int hm_lik_var_exp(cudaStream_t s, int prec, const hmogp_lik_desc& lik, int64_t N, const double* Y, const double* Mf,
                    const double* Vf, double* VE, double* dm, double* dv) {
     if (N <= 0) return 0;
@@ -239,6 +239,121 @@ int hm_lik_var_exp(cudaStream_t s, int prec, const hmogp_lik_desc& lik, int64_t 
         lik_varexp_kernel<double><<<(unsigned)nb, HM_LIK_THREADS, 0, s>>>(lik.kind, lik.K, lik.sigma, F, N, Y, Mf, Vf, VE, dm, dv);
     else
         lik_varexp_kernel<float><<<(unsigned)nb, HM_LIK_THREADS, 0, s>>>(lik.kind, lik.K, lik.sigma, F, N, Y, Mf, Vf, VE, dm, dv);
+    HM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ predictive moments (fp64)
+// likelihoods/<name>.py predictive(m, v): mean and variance of p(y*) under q(f*) = N(m, diag v), by Gauss-Hermite
+// quadrature of the likelihood's mean / variance / mean_sq functions (bernoulli.py:38-57,113-128, poisson.py:36-49,
+// 97-112, exponential.py:34-50,101-117, hetgaussian.py:75-88, gaussian.py:64-67, gamma.py:52-78,196-238,
+// beta.py:47-74,199-241, categorical.py:89-100,224-269).  Quirks kept: Gamma / Beta divide by pi twice (gh_w is
+// pre-normalised and the contraction divides again); Categorical normalises the K-1 explicit class probabilities among
+// themselves (rho_k) and returns a zero variance ("NOT IMPLEMENTED" in the reference).  `T2` = nodes per axis of the
+// tensor grids: the reference's instances cache the first table they build, 10 once var_exp has run.
+__device__ __forceinline__ void gh_table(int T, const double*& x, const double*& w) {
+    if (T == 10) { x = c_gh10_x; w = c_gh10_w; } else { x = c_gh20_x; w = c_gh20_w; }
+}
+
+__global__ void __launch_bounds__(HM_LIK_THREADS) lik_predictive_kernel(int kind, int K, double sigma, int F, int P, int T1, int T2,
+                                                                        int64_t N, const double* __restrict__ Mf,
+                                                                        const double* __restrict__ Vf, double* mean_pred,
+                                                                        double* var_pred) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= N) return;
+    const double* m = Mf + row * F;
+    const double* v = Vf + row * F;
+    double* mp = mean_pred + row * P;
+    double* vp = var_pred + row * P;
+    const double* x1; const double* w1;
+    gh_table(T1, x1, w1);
+    if (kind == HMOGP_LIK_GAUSSIAN) {
+        mp[0] = m[0];
+        vp[0] = sigma * sigma + v[0];
+    } else if (kind == HMOGP_LIK_HETGAUSSIAN) {
+        const double s1 = sqrt(2.0 * v[0]), s2 = sqrt(2.0 * v[1]);
+        double e2 = 0.0, q1 = 0.0;
+        for (int i = 0; i < T1; ++i) {
+            const double f1 = x1[i] * s1 + m[0], f2 = x1[i] * s2 + m[1];
+            e2 += hm_safe_exp(f2) * w1[i];
+            const double f1c = fmin(f1, 1.3407807929942596e154);     // GPy safe_square: min(f, sqrt(DBL_MAX))^2
+            q1 += f1c * f1c * w1[i];
+        }
+        mp[0] = m[0];
+        vp[0] = e2 + q1 - m[0] * m[0];
+    } else if (kind == HMOGP_LIK_BERNOULLI || kind == HMOGP_LIK_POISSON || kind == HMOGP_LIK_EXPONENTIAL) {
+        const double s = sqrt(2.0 * v[0]);
+        double mean = 0.0, var = 0.0, msq = 0.0;
+        for (int i = 0; i < T1; ++i) {
+            const double f = x1[i] * s + m[0];
+            double mu, va;
+            if (kind == HMOGP_LIK_BERNOULLI) {
+                const double ef = hm_safe_exp(f);
+                const double p = hm_clip(ef / (1.0 + ef), 1e-9, 1.0 - 1e-9);
+                mu = p; va = p * (1.0 - p);
+            } else if (kind == HMOGP_LIK_POISSON) {
+                mu = hm_safe_exp(f); va = mu;
+            } else {
+                const double b = hm_clip(hm_safe_exp(-f), 1e-9, 1e9);
+                mu = b; va = b * b;
+            }
+            mean += mu * w1[i];
+            var += va * w1[i];
+            msq += mu * mu * w1[i];
+        }
+        mp[0] = mean;
+        vp[0] = var + msq - mean * mean;
+    } else if (kind == HMOGP_LIK_GAMMA || kind == HMOGP_LIK_BETA) {
+        const double* x2; const double* w2;
+        gh_table(T2, x2, w2);
+        const double sa = sqrt(2.0 * v[0]), sb = sqrt(2.0 * v[1]);
+        double mean = 0.0, var = 0.0, msq = 0.0;
+        for (int i = 0; i < T2; ++i) {
+            const double a = hm_clip(hm_safe_exp(x2[i] * sa + m[0]), 1e-9, 1e9);
+            double mi = 0.0, vi = 0.0, qi = 0.0;
+            for (int j = 0; j < T2; ++j) {
+                const double b = hm_clip(hm_safe_exp(x2[j] * sb + m[1]), 1e-9, 1e9);
+                double mu, va;
+                if (kind == HMOGP_LIK_GAMMA) { mu = a / b; va = a / (b * b); }
+                else { mu = a / (a + b); va = a * b / ((a + b) * (a + b) * (a + b + 1.0)); }
+                mi += mu * w2[j]; vi += va * w2[j]; qi += mu * mu * w2[j];
+            }
+            mean += mi * w2[i]; var += vi * w2[i]; msq += qi * w2[i];
+        }
+        const double inv_pi = 1.0 / CUDART_PI;       // the second normalisation (quirk C-2)
+        mean *= inv_pi; var *= inv_pi; msq *= inv_pi;
+        mp[0] = mean;
+        const double mc = fmin(mean, 1.3407807929942596e154);
+        vp[0] = var + msq - mc * mc;
+    } else if (kind == HMOGP_LIK_CATEGORICAL) {
+        const double* x2; const double* w2;
+        gh_table(T2, x2, w2);
+        const int D = K - 1;
+        double sd[HM_MAXF], acc[HM_MAXF];
+        int idx[HM_MAXF];
+        for (int d = 0; d < D; ++d) { sd[d] = sqrt(2.0 * v[d]); acc[d] = 0.0; idx[d] = 0; }
+        int64_t npts = 1;
+        for (int d = 0; d < D; ++d) npts *= T2;
+        for (int64_t g = 0; g < npts; ++g) {
+            double e[HM_MAXF], den = 1.0, wt = 1.0;
+            for (int d = 0; d < D; ++d) { e[d] = hm_safe_exp(x2[idx[d]] * sd[d] + m[d]); den += e[d]; wt *= w2[idx[d]]; }
+            double rho[HM_MAXF], rs = 0.0;
+            for (int d = 0; d < D; ++d) { rho[d] = hm_clip(e[d] / den, 1e-9, 1.0 - 1e-9); rs += rho[d]; }
+            for (int d = 0; d < D; ++d) acc[d] += wt * (rho[d] / rs);
+            for (int d = D - 1; d >= 0; --d) { if (++idx[d] < T2) break; idx[d] = 0; }
+        }
+        for (int d = 0; d < D; ++d) { mp[d] = acc[d]; vp[d] = 0.0; }
+    }
+}
+
+int hm_lik_predictive(cudaStream_t s, const hmogp_lik_desc& lik, int gh_tensor, int64_t N, const double* Mf, const double* Vf,
+                      double* mean_pred, double* var_pred) {
+    if (N <= 0) return 0;
+    if (gh_tensor != 10 && gh_tensor != 20) { hm_set_error("hm_lik_predictive: Gauss-Hermite order %d (10 or 20)", gh_tensor); return HMOGP_ERR_ARG; }
+    const int F = lik_dimf(lik);
+    const int P = (lik.kind == HMOGP_LIK_CATEGORICAL) ? lik.K - 1 : 1;
+    lik_predictive_kernel<<<(unsigned)hm_cdiv(N, HM_LIK_THREADS), HM_LIK_THREADS, 0, s>>>(lik.kind, lik.K, lik.sigma, F, P, 20, gh_tensor, N,
+                                                                                         Mf, Vf, mean_pred, var_pred);
     HM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -59,7 +59,8 @@ template <int XD>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_bwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const HmTcInfo* __restrict__ info, int64_t nsuper,
               double* __restrict__ colpart, int npass) {
-    constexpr int R = 2 * XD + 1;     // generator table rows per 8 columns: -s z (hi, lo) per dim, -(log2 sigma^2 + kexp)
+    constexpr int R = 2 * XD;         // generator table rows per 8 columns: -s z (hi, lo) per dim (the bias is a register; a
+                                      // padded column has -s z = -1e18: d.d = 1e36 and ex2 gives exactly 0)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int Mc = pa.Mc, Mp = pa.Mp, M = pa.M, Q = pa.Q;
@@ -86,11 +87,11 @@ tc_bwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
             const double z = (m < M) ? pa.Zp[((size_t)q * Mp + m) * XD + i] : 0.0;
             float h, l;
             split_scaled(z, sscale, h, l);
-            t8[(2 * i) * 8] = -h;
-            t8[(2 * i + 1) * 8] = -l;
+            t8[(2 * i) * 8] = (m < M || i > 0) ? -h : -1.0e18f;
+            t8[(2 * i + 1) * 8] = (m < M) ? -l : 0.f;
         }
-        t8[(2 * XD) * 8] = (m < M) ? -(lv + (float)kexp) : 1.0e30f;
     }
+    const float2 gen_bias = dup2(-(lv + (float)kexp));
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&sb->full[s], kGenWarps + 1 + (rank == 0 ? 1 : 0)); mbar_init(&sb->empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&sb->tfull[b], 1); mbar_init(&sb->tempty[b], kEpiWarps * 2); }
@@ -107,19 +108,32 @@ tc_bwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
         const int rg = warp & 1, cq = warp >> 1;
         const int r0 = rg * 64 + lane, r1 = r0 + 32;
         int stage = 0; uint32_t phase = 0;
+        const int ra = (int)rank * kRows + r0, rb_ = (int)rank * kRows + r1;      // rows within the super-tile
+        // the rows' inputs of the NEXT super-tile are fetched while this one is generated
+        double xa_n[XD], xb_n[XD];
+        auto fetch_x = [&](int64_t st) {
+#pragma unroll
+            for (int i = 0; i < XD; ++i) { xa_n[i] = 0.0; xb_n[i] = 0.0; }
+            if (st >= nsuper) st = pair;                 // wraps to the first super-tile of the next m-block pass
+            if (st >= nsuper) return;
+            const SuperRef sr = find_super(tk, st);
+#pragma unroll
+            for (int i = 0; i < XD; ++i) {
+                if (ra < sr.nrows) xa_n[i] = tk.X[sr.t][(tk.begin[sr.t] + sr.row0 + ra) * XD + i];
+                if (rb_ < sr.nrows) xb_n[i] = tk.X[sr.t][(tk.begin[sr.t] + sr.row0 + rb_) * XD + i];
+            }
+        };
+        fetch_x(pair);
         for (int jm = 0; jm < njobs; ++jm) {
             for (int64_t st = pair; st < nsuper; st += npairs) {
-                const SuperRef sr = find_super(tk, st);
-                const int ra = (int)rank * kRows + r0, rb_ = (int)rank * kRows + r1;      // rows within the super-tile
                 float2 xh0[XD], xl0[XD], xh1[XD], xl1[XD];
 #pragma unroll
                 for (int i = 0; i < XD; ++i) {
-                    const double xa = (ra < sr.nrows) ? tk.X[sr.t][(tk.begin[sr.t] + sr.row0 + ra) * XD + i] : 0.0;
-                    const double xb = (rb_ < sr.nrows) ? tk.X[sr.t][(tk.begin[sr.t] + sr.row0 + rb_) * XD + i] : 0.0;
                     float h, l;
-                    split_scaled(xa, sscale, h, l); xh0[i] = dup2(h); xl0[i] = dup2(l);
-                    split_scaled(xb, sscale, h, l); xh1[i] = dup2(h); xl1[i] = dup2(l);
+                    split_scaled(xa_n[i], sscale, h, l); xh0[i] = dup2(h); xl0[i] = dup2(l);
+                    split_scaled(xb_n[i], sscale, h, l); xh1[i] = dup2(h); xl1[i] = dup2(l);
                 }
+                fetch_x(st + npairs);
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait_warp(&sb->empty[stage], phase ^ 1);
                     uint8_t* k0_hi = stage_base + (size_t)stage * kStageBytes + r0 * 128;
@@ -129,13 +143,8 @@ tc_bwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
                         const int c = cq * 2 + cc;
                         const float4* t4 = reinterpret_cast<const float4*>(tab + (size_t)(kb * 8 + c) * R * 8);
                         float2 e0[4], e1[4];
-                        {
-                            const float4 b0 = t4[(2 * XD) * 2], b1 = t4[(2 * XD) * 2 + 1];
-                            e0[0] = make_float2(b0.x, b0.y); e0[1] = make_float2(b0.z, b0.w);
-                            e0[2] = make_float2(b1.x, b1.y); e0[3] = make_float2(b1.z, b1.w);
 #pragma unroll
-                            for (int p = 0; p < 4; ++p) e1[p] = e0[p];
-                        }
+                        for (int p = 0; p < 4; ++p) e0[p] = e1[p] = gen_bias;
 #pragma unroll
                         for (int i = 0; i < XD; ++i) {
                             const float4 h0 = t4[(2 * i) * 2], h1 = t4[(2 * i) * 2 + 1];
@@ -339,7 +348,7 @@ tc_bwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
 }
 
 size_t bwd_smem_bytes(int Mc, int Xd) {
-    return (size_t)kStages * kStageBytes + sizeof(float) * ((size_t)Mc * (2 * Xd + 1) + (2 * Xd + 3) * kSuper) + sizeof(BwdBars) + 64 + 1024;
+    return (size_t)kStages * kStageBytes + sizeof(float) * ((size_t)Mc * (2 * Xd) + (2 * Xd + 3) * kSuper) + sizeof(BwdBars) + 64 + 1024;
 }
 
 template <int XD>

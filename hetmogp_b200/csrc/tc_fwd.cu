@@ -118,10 +118,12 @@ __device__ __forceinline__ void two_sum_add(float& hi, float& lo, float x) {
 }
 
 // Per-column constants, grouped by 8 columns so that one thread fetches them with 128-bit loads:
-//   tab[chunk8][row][8]   rows: 2i = -s z_i (hi), 2i+1 = -s z_i (lo), 2XD = -(log2 sigma^2 + kexp) (generator bias),
-//                               2XD+1 = -log2 sigma^2 (epilogue bias), 2XD+2 = alpha_q;  padded columns: biases +1e30
-// (negated so that the packed loops are pure FADD2 / FFMA2:  K = ex2(-(d.d - bias)))
-template <int XD> struct FwdTab { static constexpr int R = 2 * XD + 3; };
+//   tab[chunk8][row][8]   rows: 2i = -s z_i (hi), 2i+1 = -s z_i (lo), 2XD = alpha_q
+// (negated so that the packed loops are pure FADD2 / FFMA2:  K = ex2(-(d.d - bias))).  The biases are the same for every
+// column (-(log2 sigma^2 + kexp) in the generator, -log2 sigma^2 in the epilogue) and travel in registers; a padded
+// column has -s z = -1e18 on its first coordinate, so d.d = 1e36 and ex2 gives exactly 0 (shared-memory wavefronts, not
+// issue slots, bound this kernel: every table row dropped is 12 % of its LSU traffic).
+template <int XD> struct FwdTab { static constexpr int R = 2 * XD + 1; };
 
 template <int XD, int NCTA, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -156,14 +158,13 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
             const double z = (m < M) ? pa.Zp[((size_t)q * Mp + m) * XD + i] : 0.0;
             float h, l;
             split_scaled(z, sscale, h, l);
-            t8[(2 * i) * 8] = -h;
-            t8[(2 * i + 1) * 8] = -l;
+            t8[(2 * i) * 8] = (m < M || i > 0) ? -h : -1.0e18f;
+            t8[(2 * i + 1) * 8] = (m < M) ? -l : 0.f;
         }
-        const float lv = (float)log2(cs->var[q]);
-        t8[(2 * XD) * 8] = (m < M) ? -(lv + (float)kexp) : 1.0e30f;
-        t8[(2 * XD + 1) * 8] = (m < M) ? -lv : 1.0e30f;
-        t8[(2 * XD + 2) * 8] = (m < M) ? (float)pa.alpha[(size_t)q * Mp + m] : 0.f;
+        t8[(2 * XD) * 8] = (m < M) ? (float)pa.alpha[(size_t)q * Mp + m] : 0.f;
     }
+    const float lv_ = (float)log2(cs->var[q]);
+    const float2 gen_bias = dup2(-(lv_ + (float)kexp)), epi_bias = dup2(-lv_);
     if (threadIdx.x == 0) {
         // full: generator warps + bulk-copy expect_tx (+ on the leader of a pair: the peer's relay)
         for (int s = 0; s < kStages; ++s) { mbar_init(&sb->full[s], kGenWarps + 1 + ((NCTA == 2 && rank == 0) ? 1 : 0)); mbar_init(&sb->empty[s], 1); }
@@ -182,17 +183,30 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
         const int rg = warp & 1, cq = warp >> 1;
         const int r0 = rg * 64 + lane, r1 = r0 + 32;
         int stage = 0; uint32_t phase = 0;
-        for (int64_t st_ = step0; st_ < nsteps; st_ += dstep) {
+        // the rows' inputs of the NEXT tile are fetched while this one is generated (an exposed HBM round trip per tile
+        // was ~4 % of the kernel)
+        double xa_n[XD], xb_n[XD];
+        auto fetch_x = [&](int64_t st_) {
+#pragma unroll
+            for (int i = 0; i < XD; ++i) { xa_n[i] = 0.0; xb_n[i] = 0.0; }
+            if (st_ >= nsteps) return;
             const TileRef tr = find_tile(tk, st_ * NCTA + rank);
+#pragma unroll
+            for (int i = 0; i < XD; ++i) {
+                if (r0 < tr.nrows) xa_n[i] = tk.X[tr.t][(tk.begin[tr.t] + tr.row0 + r0) * XD + i];
+                if (r1 < tr.nrows) xb_n[i] = tk.X[tr.t][(tk.begin[tr.t] + tr.row0 + r1) * XD + i];
+            }
+        };
+        fetch_x(step0);
+        for (int64_t st_ = step0; st_ < nsteps; st_ += dstep) {
             float2 xh0[XD], xl0[XD], xh1[XD], xl1[XD];
 #pragma unroll
             for (int i = 0; i < XD; ++i) {
-                const double xa = (r0 < tr.nrows) ? tk.X[tr.t][(tk.begin[tr.t] + tr.row0 + r0) * XD + i] : 0.0;
-                const double xb_ = (r1 < tr.nrows) ? tk.X[tr.t][(tk.begin[tr.t] + tr.row0 + r1) * XD + i] : 0.0;
                 float h, l;
-                split_scaled(xa, sscale, h, l); xh0[i] = dup2(h); xl0[i] = dup2(l);
-                split_scaled(xb_, sscale, h, l); xh1[i] = dup2(h); xl1[i] = dup2(l);
+                split_scaled(xa_n[i], sscale, h, l); xh0[i] = dup2(h); xl0[i] = dup2(l);
+                split_scaled(xb_n[i], sscale, h, l); xh1[i] = dup2(h); xl1[i] = dup2(l);
             }
+            fetch_x(st_ + dstep);
             for (int h = 0; h < nhalf; ++h) {
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait_warp(&sb->empty[stage], phase ^ 1);
@@ -203,13 +217,8 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
                         const int c = cq * 2 + cc;
                         const float4* t4 = reinterpret_cast<const float4*>(tab + (size_t)(kb * 8 + c) * R * 8);
                         float2 e0[4], e1[4];   // d.d - bias for the 8 columns (4 pairs), rows r0 / r1
-                        {
-                            const float4 b0 = t4[(2 * XD) * 2], b1 = t4[(2 * XD) * 2 + 1];
-                            e0[0] = make_float2(b0.x, b0.y); e0[1] = make_float2(b0.z, b0.w);
-                            e0[2] = make_float2(b1.x, b1.y); e0[3] = make_float2(b1.z, b1.w);
 #pragma unroll
-                            for (int p = 0; p < 4; ++p) e1[p] = e0[p];
-                        }
+                        for (int p = 0; p < 4; ++p) e0[p] = e1[p] = gen_bias;
 #pragma unroll
                         for (int i = 0; i < XD; ++i) {
                             const float4 h0 = t4[(2 * i) * 2], h1 = t4[(2 * i) * 2 + 1];
@@ -249,14 +258,23 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
         const float inv_pc = pow2i(-(kexp + cexp));      // undo the operand scales of P
         const float inv_s2 = (float)(1.0 / s2);           // scaled squared distance -> |x - z|^2
         uint32_t jc = 0, tcount = 0;
+        double x_n[XD];
+        auto fetch_x = [&](int64_t st_) {
+#pragma unroll
+            for (int i = 0; i < XD; ++i) x_n[i] = 0.0;
+            if (st_ >= nsteps) return;
+            const TileRef tn = find_tile(tk, st_ * NCTA + rank);
+#pragma unroll
+            for (int i = 0; i < XD; ++i)
+                if (r < tn.nrows) x_n[i] = tk.X[tn.t][(tk.begin[tn.t] + tn.row0 + r) * XD + i];
+        };
+        fetch_x(step0);
         for (int64_t st_ = step0; st_ < nsteps; st_ += dstep, ++tcount) {
             const TileRef tr = find_tile(tk, st_ * NCTA + rank);
             float xh[XD], xl[XD];
 #pragma unroll
-            for (int i = 0; i < XD; ++i) {
-                const double x = (r < tr.nrows) ? tk.X[tr.t][(tk.begin[tr.t] + tr.row0 + r) * XD + i] : 0.0;
-                split_scaled(x, sscale, xh[i], xl[i]);
-            }
+            for (int i = 0; i < XD; ++i) split_scaled(x_n[i], sscale, xh[i], xl[i]);
+            fetch_x(st_ + dstep);
             float ah = 0.f, al = 0.f, chh = 0.f, cl = 0.f, bh = 0.f, bl = 0.f, eh = 0.f, el = 0.f;
             for (int h = 0; h < nhalf; ++h, ++jc) {
                 const uint32_t buf = jc & 1u;
@@ -287,13 +305,11 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
                                 u[p] = (i == 0) ? mul2(d, d) : fma2(d, d, u[p]);
                             }
                         }
-                        const float4 b0 = t4[(2 * XD + 1) * 2], b1 = t4[(2 * XD + 1) * 2 + 1];
-                        const float4 q0 = t4[(2 * XD + 2) * 2], q1 = t4[(2 * XD + 2) * 2 + 1];
-                        const float2 nb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+                        const float4 q0 = t4[(2 * XD) * 2], q1 = t4[(2 * XD) * 2 + 1];
                         const float2 aa[4] = {make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y), make_float2(q1.z, q1.w)};
 #pragma unroll
                         for (int p = 0; p < 4; ++p) {
-                            const float2 ea = add2(u[p], nb[p]);                       // d.d - log2 sigma^2
+                            const float2 ea = add2(u[p], epi_bias);                    // d.d - log2 sigma^2
                             const float2 kv = make_float2(ex2(-ea.x), ex2(-ea.y));
                             const float2 pk = mul2(make_float2(__uint_as_float(v[g * 8 + 2 * p]), __uint_as_float(v[g * 8 + 2 * p + 1])), kv);
                             const float2 ak = mul2(kv, aa[p]);
@@ -407,7 +423,7 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
 }
 
 template <int NCTA> size_t fwd_smem_bytes(int Mc, int Xd, int stages) {
-    return (size_t)stages * FwdCfg<NCTA>::stage_bytes + sizeof(float) * ((size_t)Mc * (2 * Xd + 3) + 2 * 4 * 128) +
+    return (size_t)stages * FwdCfg<NCTA>::stage_bytes + sizeof(float) * ((size_t)Mc * (2 * Xd + 1) + 2 * 4 * 128) +
            sizeof(FwdBars) + 64 + 1024;
 }
 

@@ -61,17 +61,27 @@ constexpr int kPhases = HM_G2_PHASES;               // generator warp groups on 
 constexpr int kPhaseWarps = kGenWarps / kPhases;    // 4 column groups x (4 / kPhases) row parts
 constexpr int kGroups = 2 * kPhases;                // groups of 8 rows per thread and chunk
 constexpr int kLoaders = HM_G2_LOADERS;
-constexpr int kThreads = (kGenWarps + 1 + kLoaders) * 32;
-constexpr uint32_t kAcc2 = 256;                    // TMEM column of the level-2 accumulator
+constexpr int kFoldWarps = 4;                       // one per TMEM lane quadrant (a warp reaches lanes 32 (warp % 4) .. + 31)
+constexpr int kFoldWarp0 = kGenWarps + 1 + kLoaders;
+constexpr int kThreads = (kGenWarps + 1 + kLoaders + kFoldWarps) * 32;
+static_assert(kFoldWarp0 % 4 == 0, "fold warp w serves TMEM lane quadrant w % 4");
+constexpr uint32_t kAccCols = 256;                 // TMEM columns per accumulator buffer (two buffers: windows alternate)
+#ifndef HM_G2_CARRY
+#define HM_G2_CARRY 0.75f                          // a window starts at -HM_G2_CARRY times the buffer's previous final value
+#endif
 static_assert(kC == 64, "SWIZZLE_128B operand rows hold 64 fp16 values");
 
-struct Pending { double* slot; double inv_sc; uint32_t parity; int nfold; bool to_l3, slot_fresh; };   // a deferred window fold (nfold: windows already in level 2)
 struct Bars {
-    uint64_t full[kStages], empty[kStages], rowfull[kRowSlots], rowempty[kRowSlots], accfull, accempty;
+    uint64_t full[kStages], empty[kStages], rowfull[kRowSlots], rowempty[kRowSlots], accfull[2], accempty[2];
     uint32_t sflag[kStages];   // sign class of the chunk in the stage (for the MMA issuer)
     uint32_t tmem_base;
-    Pending pend[kGenWarps];   // warp-uniform; kept out of the register file
 };
+
+// fp64 partial tile of a (segment, CTA): element (row i < 128, column j < 256) of the block.  Laid out so that the 32 lanes
+// of a fold warp (consecutive rows, the same column pair) touch 512 consecutive bytes: [j / 16][(j % 16) / 2][i][j % 2].
+__device__ __host__ __forceinline__ size_t slot_index(int i, int j) {
+    return ((size_t)((j >> 4) * 8 + ((j & 15) >> 1)) * 128 + i) * 2 + (j & 1);
+}
 
 // exponent se with max sqrt|w| 2^se <= 4 (operands then stay below 2^14: K 2^kexp < 2^12)
 __device__ __forceinline__ int weight_exp(const HmTcInfo* info, int q) {
@@ -121,7 +131,7 @@ __device__ __forceinline__ void split2r(float2 v, uint32_t& hi, uint32_t& lo, fl
 }
 
 template <int XD, int NV>
-__global__ void __launch_bounds__(kThreads, 1)   // 96 registers: the file is allocated for 20 warps (18 rounded up to 4s)
+__global__ void __launch_bounds__(kThreads, 1)   // 24 warps: 80 registers per thread (the generators, rid of the folds, fit)
 tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, const HmGramSeg* __restrict__ segs,
                 const int* __restrict__ seg_off, double* __restrict__ slots, int f1, int f2, int npass) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -142,8 +152,10 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
         // read the stage have completed; rowfull / rowempty: row-data ring between the loader and the generators
         for (int s = 0; s < kStages; ++s) { mbar_init(&sb->full[s], kPhaseWarps + (rank == 0 ? 1 : 0)); mbar_init(&sb->empty[s], 1); }
         for (int s = 0; s < kRowSlots; ++s) { mbar_init(&sb->rowfull[s], 1); mbar_init(&sb->rowempty[s], kPhaseWarps); }
-        mbar_init(&sb->accfull, 1);
-        mbar_init(&sb->accempty, 2 * kGenWarps);   // used on the leader: both CTAs' flush warps
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&sb->accfull[b], 1);
+            mbar_init(&sb->accempty[b], 2 * kFoldWarps);  // used on the leader: both CTAs' fold warps
+        }
         mbar_fence_init();
     }
     if (warp == kMmaWarp) tmem_alloc2(&sb->tmem_base, 512u);
@@ -153,78 +165,12 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
     const uint32_t tmem_base = sb->tmem_base;
 
     if (warp < kGenWarps) {
-        // ======================================================= generators (+ level-2/3 flushes)
+        // ======================================================= generators
         const int cgp = warp & 3, rh = (warp % kPhaseWarps) >> 2, rp = warp >> 2;   // column group, row part of the chunk, partial index
         const uint32_t phase = (uint32_t)warp / kPhaseWarps;
         const int col = cgp * 32 + lane;                  // operand row (inducing point within this CTA's 128) this thread writes
         const int swz = col & 7;                          // SW128: 16-byte chunk ^= row & 7
         uint32_t cc_ = 0;     // chunk counter (stage / row-slot rings)
-        uint32_t iv = 0;      // level-1 window counter (accumulator barriers)
-        bool pend_on = false;
-        uint32_t pend_parity = 0;
-        Pending* pend = &sb->pend[warp];
-        // fold one finished level-1 window (TMEM cols [0,256)) into level 2 (TMEM cols [256,512), fp32 round-to-nearest)
-        // or, every f2 windows / at the end of a segment, level 1 + level 2 into the fp64 partial tile
-        // Centred accumulation.  tcgen05 accumulates with truncation: every MMA loses up to one ulp of the running sum
-        // TOWARDS ZERO, a bias that grows with the window length and that K_uu^-1 . K_uu^-1 amplifies.  The
-        // sums of a window all have one sign (V^T V with the sign of omega), so the accumulator of window w is started
-        // at I_w = -mean(previous window sums) / 2 instead of 0: it runs from -S/2 to +S/2 and the truncation bias of the
-        // two halves cancels.  I_w is a deterministic function of level 2 (which is read anyway), so the fold recomputes
-        // it instead of storing it.  The first window after every fp64 flush starts at 0.
-        auto flush_window = [&]() {
-            const Pending pd = *pend;
-            mbar_wait_warp(&sb->accfull, pd.parity);
-            fence_after();
-            const int lq = warp & 3, wq = warp >> 2;
-            const int i = lq * 32 + lane;
-            const uint32_t tl = tmem_base + ((uint32_t)(lq * 32) << 16);
-            const float init_prev = HM_G2_CENTRE && pd.nfold > 0 ? -0.5f / (float)pd.nfold : 0.f;      // I_w = init_prev * L2_old
-            const float init_next = HM_G2_CENTRE ? -0.5f / (float)(pd.nfold + 1) : 0.f;                // I_{w+1} = init_next * L2_new
-            for (int c16 = wq; c16 < 16; c16 += kGenWarps / 4) {   // units of 16 columns
-                uint32_t v[16];
-                tmem_ld16(tl + c16 * 16, v);
-                if (pd.nfold > 0) {
-                    uint32_t u[16];
-                    tmem_ld16(tl + kAcc2 + c16 * 16, u);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int p = 0; p < 16; ++p) {
-                        const float l2 = __uint_as_float(u[p]);
-                        v[p] = __float_as_uint((__uint_as_float(v[p]) - init_prev * l2) + l2);   // level 2 += window sum
-                    }
-                } else {
-                    tmem_ld_wait();
-                }
-                if (!pd.to_l3) {
-                    tmem_st16(tl + kAcc2 + c16 * 16, v);
-                    if (HM_G2_CENTRE) {
-                        uint32_t w[16];
-#pragma unroll
-                        for (int p = 0; p < 16; ++p) w[p] = __float_as_uint(init_next * __uint_as_float(v[p]));
-                        tmem_st16(tl + c16 * 16, w);                                             // start value of the next window
-                    }
-                } else {
-                    double2* dst = reinterpret_cast<double2*>(pd.slot + ((size_t)i * 256 + c16 * 16));
-                    if (pd.slot_fresh) {
-#pragma unroll
-                        for (int p = 0; p < 8; ++p)
-                            dst[p] = make_double2((double)__uint_as_float(v[2 * p]) * pd.inv_sc, (double)__uint_as_float(v[2 * p + 1]) * pd.inv_sc);
-                    } else {
-#pragma unroll
-                        for (int p = 0; p < 8; ++p) {
-                            double2 o = dst[p];
-                            o.x += (double)__uint_as_float(v[2 * p]) * pd.inv_sc;
-                            o.y += (double)__uint_as_float(v[2 * p + 1]) * pd.inv_sc;
-                            dst[p] = o;
-                        }
-                    }
-                }
-            }
-            if (!pd.to_l3) tmem_st_wait();
-            fence_before();
-            __syncwarp();
-            if (lane == 0) { if (rank == 0) mbar_arrive(&sb->accempty); else mbar_arrive_remote(&sb->accempty, 0); }
-        };
         for (int sgi = seg_begin; sgi < seg_end; ++sgi) {
             const HmGramSeg sg = segs[sgi];
             const int q = sg.q;
@@ -252,21 +198,12 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
             const double inv_sc = (double)pow2i(-2 * se) * (cs->var[q] / ksc) * (cs->var[q] / ksc);   // D = (ksc / var)^2 2^(2 se) H
             const double inv_k = cs->var[q];
             double* slot = slots + (size_t)(2 * sg.slot + (int)rank) * HM_GRAM_SLOT_DOUBLES;
-            bool slot_fresh = true;    // level 3: first flush of the segment stores, later ones add
-            int nfold = 0;             // level 2: windows it holds
-            int win = 0;
 
-            for (int c0 = sg.chunk_begin; c0 < sg.chunk_end; c0 += f1, ++win) {
+            for (int c0 = sg.chunk_begin; c0 < sg.chunk_end; c0 += f1) {
                 const int c1 = min(sg.chunk_end, c0 + f1);
                 for (int c = c0; c < c1; ++c, ++cc_) {
                     if (kPhases > 1 && (cc_ % kPhases) != phase) continue;
                     const int stage = cc_ % kStages, rs = cc_ % kRowSlots;
-                    if (pend_on) {   // fold the previous window as soon as its MMAs are done, or before we would block on them
-                        if (mbar_test(&sb->accfull, pend_parity) || !mbar_test(&sb->empty[stage], ((cc_ / kStages) & 1u) ^ 1u)) {
-                            flush_window();
-                            pend_on = false;
-                        }
-                    }
                     mbar_wait_warp(&sb->rowfull[rs], (cc_ / kRowSlots) & 1u);
                     mbar_wait_warp(&sb->empty[stage], ((cc_ / kStages) & 1u) ^ 1u);
                     const float* rb = rowbuf + (size_t)rs * kC * kRowArrays;   // SoA: array a at rb + a * kC
@@ -356,26 +293,69 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
                         mbar_arrive(&sb->rowempty[rs]);
                     }
                 }
-                // ---- end of a level-1 window: its fold into level 2 / 3 is deferred (see flush_window) so that the
-                //      generators keep the smem ring full while the MMAs of the window drain
-                if (NV > 0 && sg.has_g) { g64 += (double)(g2.x + g2.y); g2 = dup2(0.f); }
-                if (pend_on) flush_window();
-                pend_on = true;
-                pend_parity = iv & 1u;
-                const bool to_l3 = ((win + 1) % f2 == 0) || (c1 == sg.chunk_end);
-                __syncwarp();
-                if (lane == 0) {
-                    pend->to_l3 = to_l3; pend->slot_fresh = slot_fresh; pend->nfold = nfold;
-                    pend->slot = slot; pend->inv_sc = inv_sc; pend->parity = pend_parity;
-                }
-                __syncwarp();
-                if (to_l3) { slot_fresh = false; nfold = 0; } else ++nfold;
-                ++iv;
+                if (NV > 0 && sg.has_g) { g64 += (double)(g2.x + g2.y); g2 = dup2(0.f); }   // fp32 partial per window
             }
             if (NV > 0 && sg.has_g) slot[(size_t)128 * 256 + rp * 128 + col] = g64 * inv_k;   // one partial per row part
             if (diag) slot[(size_t)128 * 256 + 512 + rp * 128 + col] = (double)(cacc.x + cacc.y) * inv_sc;
         }
-        if (pend_on) flush_window();
+    } else if (warp >= kFoldWarp0) {
+        // ======================================================= fold warps: finished accumulator windows -> fp64 partial tile
+        // The 512 TMEM columns hold TWO fp32 accumulators of the 256 x 256 block; windows of f1 chunks alternate between
+        // them, so the MMAs of window w + 1 run while window w is moved out here -- one tcgen05.ld pass over the buffer and a
+        // coalesced read-modify-write of the segment's (L2-resident) fp64 tile -- and the generators never stop.  A fold
+        // has a whole window of MMA time to finish, so four warps with a few loads in flight are enough.
+        // tcgen05 accumulates with truncation: every MMA loses up to one ulp of the running sum TOWARDS ZERO, a bias that
+        // grows with the window length and that K_uu^-1 . K_uu^-1 amplifies.  The sums of a window all have one
+        // sign (V^T V with the sign of omega), so a buffer's next window does not start at 0 but at -c times the value v the
+        // buffer ended this one with (c = HM_G2_CARRY): the accumulator then runs from about -0.43 S to +0.57 S and most of
+        // the bias cancels.  The bookkeeping is exact and needs no storage: with v_w = I_w + S_w and I_w = -c v_{w-2},
+        // sum_w S_w = sum_w (1 + c [window w + 2 of this segment exists]) v_w, accumulated in fp64.
+        const int lq = warp & 3;
+        const int i = lq * 32 + lane;
+        uint32_t iv = 0;
+        for (int sgi = seg_begin; sgi < seg_end; ++sgi) {
+            const HmGramSeg sg = segs[sgi];
+            const int q = sg.q;
+            const int se = weight_exp(info, q);
+            const double ksc = (double)((float)cs->var[q] * pow2i(info->kexp[q]));              // as the loader rounds it
+            const double inv_sc = (double)pow2i(-2 * se) * (cs->var[q] / ksc) * (cs->var[q] / ksc);   // D = (ksc / var)^2 2^(2 se) H
+            double* slot = slots + (size_t)(2 * sg.slot + (int)rank) * HM_GRAM_SLOT_DOUBLES;
+            for (int c0 = sg.chunk_begin; c0 < sg.chunk_end; c0 += f1, ++iv) {
+                const uint32_t buf = iv & 1u;
+                const bool fresh = c0 == sg.chunk_begin;                                   // first fold of the segment stores
+                const bool carry = HM_G2_CENTRE && (c0 + 2 * f1 < sg.chunk_end);           // the buffer's next window is of this segment
+                const double sc = inv_sc * (carry ? 1.0 + (double)HM_G2_CARRY : 1.0);
+                mbar_wait_warp(&sb->accfull[buf], (iv >> 1) & 1u);
+                fence_after();
+                const uint32_t tl = tmem_base + ((uint32_t)(lq * 32) << 16) + buf * kAccCols;
+#pragma unroll 1
+                for (int c16 = 0; c16 < 16; ++c16) {
+                    uint32_t v[16];
+                    tmem_ld16(tl + c16 * 16, v);
+                    double2* dst = reinterpret_cast<double2*>(slot + slot_index(i, c16 * 16));   // + p * 128 double2 per column pair
+                    double2 o[8];
+                    if (!fresh) {
+#pragma unroll
+                        for (int p = 0; p < 8; ++p) o[p] = __ldcg(dst + p * 128);
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        const double x = (double)__uint_as_float(v[2 * p]) * sc, y = (double)__uint_as_float(v[2 * p + 1]) * sc;
+                        __stcg(dst + p * 128, fresh ? make_double2(x, y) : make_double2(o[p].x + x, o[p].y + y));
+                    }
+                    if (carry) {
+#pragma unroll
+                        for (int p = 0; p < 16; ++p) v[p] = __float_as_uint(-HM_G2_CARRY * __uint_as_float(v[p]));
+                        tmem_st16(tl + c16 * 16, v);                   // start value of this buffer's next window
+                    }
+                }
+                if (carry) tmem_st_wait();
+                fence_before();
+                __syncwarp();
+                if (lane == 0) { if (rank == 0) mbar_arrive(&sb->accempty[buf]); else mbar_arrive_remote(&sb->accempty[buf], 0); }
+            }
+        }
     } else if (warp == kMmaWarp) {
         if (lane == 0 && rank == 0) {
             // ======================================================= MMA issuer (one thread of the leader CTA)
@@ -384,11 +364,13 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
             for (int sgi = seg_begin; sgi < seg_end; ++sgi) {
                 const HmGramSeg sg = segs[sgi];
                 const bool diag = sg.j0 == sg.I * 256;
-                int nfold = 0;   // as in the generators: windows held by level 2 (then the fold pre-set the accumulator)
                 for (int c0 = sg.chunk_begin; c0 < sg.chunk_end; c0 += f1) {
                     const int c1 = min(sg.chunk_end, c0 + f1);
-                    const uint32_t preset = (HM_G2_CENTRE && nfold > 0) ? 1u : 0u;
-                    mbar_wait_cluster(&sb->accempty, (iv & 1u) ^ 1u);
+                    // the fold of this buffer's previous window pre-set the accumulator if that window was of this segment
+                    const uint32_t preset = (HM_G2_CENTRE && c0 - 2 * f1 >= sg.chunk_begin) ? 1u : 0u;
+                    const uint32_t buf = iv & 1u;
+                    const uint32_t d_tmem = tmem_base + buf * kAccCols;
+                    mbar_wait_cluster(&sb->accempty[buf], ((iv >> 1) & 1u) ^ 1u);
                     fence_after();
                     for (int c = c0; c < c1; ++c, ++cc_) {
                         const int stage = cc_ % kStages;
@@ -406,16 +388,15 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
 #pragma unroll
                         for (int ks = 0; ks < kC / 16; ++ks) {
                             const uint64_t adv = (uint64_t)(ks * 2);   // 32 bytes per K=16 step, in 16-byte units
-                            mma2_f16(tmem_base, a_hi + adv, b_hi + adv, idc, (c > c0 || ks > 0) ? 1u : preset);
-                            if (npass >= 2) mma2_f16(tmem_base, a_hi + adv, b_lo + adv, idc, 1u);
-                            if (npass >= 3 && !(HM_G2_SYMDIAG && diag)) mma2_f16(tmem_base, a_lo + adv, b_hi + adv, idc, 1u);
-                            if (npass >= 4) mma2_f16(tmem_base, a_lo + adv, b_lo + adv, idc, 1u);   // diagnostic
+                            mma2_f16(d_tmem, a_hi + adv, b_hi + adv, idc, (c > c0 || ks > 0) ? 1u : preset);
+                            if (npass >= 2) mma2_f16(d_tmem, a_hi + adv, b_lo + adv, idc, 1u);
+                            if (npass >= 3 && !(HM_G2_SYMDIAG && diag)) mma2_f16(d_tmem, a_lo + adv, b_hi + adv, idc, 1u);
+                            if (npass >= 4) mma2_f16(d_tmem, a_lo + adv, b_lo + adv, idc, 1u);   // diagnostic
                         }
                         commit2(&sb->empty[stage]);
                     }
-                    commit2(&sb->accfull);
+                    commit2(&sb->accfull[buf]);
                     ++iv;
-                    nfold = (nfold + 1 == f2 || c1 == sg.chunk_end) ? 0 : nfold + 1;   // to_l3 of the generators
                 }
             }
         } else if (lane == 0) {
@@ -536,10 +517,10 @@ __global__ void tc_gram2_reduce_kernel(const double* __restrict__ slots, const H
             const int li = r * 128 + i, lj = j;
             const int r2 = lj >> 7, i2 = lj & 127;
             for (int sl = sr.x; sl < sr.y; ++sl)
-                s += 0.5 * (slots[(size_t)(2 * sl + r) * HM_GRAM_SLOT_DOUBLES + ((size_t)i * 256 + j)] +
-                            slots[(size_t)(2 * sl + r2) * HM_GRAM_SLOT_DOUBLES + ((size_t)i2 * 256 + li)]);
+                s += 0.5 * (slots[(size_t)(2 * sl + r) * HM_GRAM_SLOT_DOUBLES + slot_index(i, j)] +
+                            slots[(size_t)(2 * sl + r2) * HM_GRAM_SLOT_DOUBLES + slot_index(i2, li)]);
         } else
-        for (int sl = sr.x; sl < sr.y; ++sl) s += slots[(size_t)(2 * sl + r) * HM_GRAM_SLOT_DOUBLES + ((size_t)i * 256 + j)];
+        for (int sl = sr.x; sl < sr.y; ++sl) s += slots[(size_t)(2 * sl + r) * HM_GRAM_SLOT_DOUBLES + slot_index(i, j)];
         if (gr == gc)   // the lo x lo term of the diagonal (see the generator)
             for (int sl = sr.x; sl < sr.y; ++sl)
                 for (int rp = 0; rp < 4; ++rp) s += slots[(size_t)(2 * sl + r) * HM_GRAM_SLOT_DOUBLES + (size_t)128 * 256 + 512 + rp * 128 + i];

@@ -1,4 +1,4 @@
-"""HetLikelihood with the reference's interface (hetmogp/het_likelihood.py:10-131, hot-path methods)."""
+"""HetLikelihood with the reference's interface (hetmogp/het_likelihood.py:10-164)."""
 import ctypes as C
 
 import numpy as np
@@ -50,3 +50,21 @@ class HetLikelihood(object):
             dm.append(a)
             dv.append(b)
         return dm, dv
+
+    def predictive(self, mu_F_pred, v_F_pred, Y_metadata):
+        """het_likelihood.py:133-148: per-task predictive mean and variance."""
+        tasks = np.unique(Y_metadata['task_index'].flatten())
+        m_pred, v_pred = [], []
+        for t in tasks:
+            m, v = self.likelihoods_list[t].predictive(mu_F_pred[t], v_F_pred[t], Y_metadata=None)
+            m_pred.append(m)
+            v_pred.append(v)
+        return m_pred, v_pred
+
+    def negative_log_predictive(self, Ytest, mu_F_star, v_F_star, Y_metadata, num_samples):
+        """het_likelihood.py:150-164: NLPD over the test data of every task."""
+        tasks = np.unique(Y_metadata['task_index'].flatten())
+        logpred = 0
+        for t in tasks:
+            logpred += self.likelihoods_list[t].log_predictive(Ytest[t], mu_F_star[t], v_F_star[t], num_samples)
+        return -logpred

@@ -3,9 +3,12 @@
 Each class mirrors the reference class of the same name: ctor, ``get_metadata() -> (dim_y, dim_f, dim_p)``,
 ``ismulti()``, ``var_exp(Y, M, V, gh_points=None, Y_metadata=None)``, ``var_exp_derivatives(...)``, ``logpdf``,
 ``dlogp_df``, ``d2logp_df2`` (Categorical's derivative methods take the leading function index ``df``,
-categorical.py:102,115; Gamma/Beta return 2-tuples, gamma.py:80-101).  Prediction/sampling methods are out of
-scope.  All numbers come from ``hmogp_lik_var_exp`` / ``hmogp_lik_pointwise``
-(hetmogp_b200/csrc/lik_kernels.cu); numpy arrays in -> numpy arrays out, torch CUDA tensors in -> tensors out.
+categorical.py:102,115; Gamma/Beta return 2-tuples, gamma.py:80-101), ``predictive(m, v)`` (Gauss-Hermite predictive
+mean / variance, e.g. bernoulli.py:113-128) and ``log_predictive(Ytest, mu_F_star, v_F_star, num_samples)`` (Monte-Carlo
+log predictive density, e.g. bernoulli.py:130-144).  All numbers come from ``hmogp_lik_var_exp`` / ``hmogp_lik_pointwise``
+/ ``hmogp_lik_predictive`` (hetmogp_b200/csrc/lik_kernels.cu); numpy arrays in -> numpy arrays out, torch CUDA tensors in
+-> tensors out.  ``log_predictive`` draws its function samples with ``numpy.random.normal`` in the reference's order and
+shapes (so a seeded run reproduces the reference's estimate) and evaluates the N x num_samples log-densities on the GPU.
 """
 import ctypes as C
 
@@ -81,6 +84,45 @@ class _Likelihood(object):
     def logpdf(self, F, y, Y_metadata=None):
         return self._pointwise(F, y)[0]
 
+    # ---- prediction (svmogp.py:340-378 -> het_likelihood.py:133-164)
+    gh_tensor = 10   # nodes per axis of the tensor grids: the reference's instance has cached the var_exp table by then
+
+    def predictive(self, m, v, gh_points=None, Y_metadata=None):
+        dy, F, P = self.get_metadata()
+        (m, v), kind, dev = self._prep(m, v)
+        N = int(m.reshape(-1, F).shape[0])
+        m, v = m.reshape(N, F), v.reshape(N, F)
+        mean, var = self._empty((N, P), dev), self._empty((N, P), dev)
+        d = self._desc()
+        check(lib.hmogp_lik_predictive(C.byref(d), N, ptr(m), ptr(v), ptr(mean), ptr(var), int(self.gh_tensor), kind, None))
+        return mean, var
+
+    _sample_layout = "NSD"   # F_samples (Ntest, num_samples, D) as bernoulli.py:131-137; "NDS" for the logpdf_sampling classes
+
+    @staticmethod
+    def _regroup(lp):
+        return lp
+
+    def log_predictive(self, Ytest, mu_F_star, v_F_star, num_samples):
+        """-log(S) + logsumexp_s log p(y_n | f_ns), summed over n and -- as the reference does -- divided by num_samples."""
+        mu_F_star, v_F_star = np.asarray(mu_F_star, dtype=np.float64), np.asarray(v_F_star, dtype=np.float64)
+        Ytest = np.asarray(Ytest, dtype=np.float64)
+        Ntest, D = mu_F_star.shape
+        S = int(num_samples)
+        Fs = np.empty((Ntest, S, D))
+        for d in range(D):                                     # the reference's draw order: one (Ntest, S) block per function
+            Fs[:, :, d] = np.random.normal(mu_F_star[:, d][:, None], np.sqrt(v_F_star[:, d][:, None]), size=(Ntest, S))
+        if self._sample_layout == "NSD" and D > 1:
+            Fs = Fs[:, :, :1]                                  # those classes evaluate logpdf(F_samples[:,:,0], Ytest)
+        Fd = Fs.shape[2]
+        yrep = np.repeat(Ytest.reshape(Ntest, 1), S, axis=1).reshape(-1)
+        lp = np.asarray(self._pointwise(Fs.reshape(Ntest * S, Fd), yrep)[0]).reshape(Ntest, S)
+        lp = self._regroup(lp)
+        mx = lp.max(axis=-1, keepdims=True)
+        mx = np.where(np.isfinite(mx), mx, 0.0)
+        log_pred = -np.log(S) + (mx[:, 0] + np.log(np.exp(lp - mx).sum(axis=-1)))
+        return (1.0 / S) * log_pred.sum()
+
 
 class _WithDerivs(_Likelihood):
     def dlogp_df(self, f, y, Y_metadata=None):
@@ -100,9 +142,10 @@ class Gaussian(_Likelihood):
 
 
 class HetGaussian(_Likelihood):
-    """likelihoods/hetgaussian.py:17-73."""
+    """likelihoods/hetgaussian.py:17-104."""
     name = "HetGaussian"
     spec = ("HetGaussian",)
+    _sample_layout = "NDS"   # logpdf_sampling, hetgaussian.py:35-39,90-104
 
     def __init__(self, gp_link=None):
         pass
@@ -139,6 +182,16 @@ class Categorical(_Likelihood):
     """likelihoods/categorical.py:22-222."""
     name = "Categorical"
 
+    _sample_layout = "NDS"   # logpdf_sampling, categorical.py:48-63,271-285
+
+    @staticmethod
+    def _regroup(lp):
+        """categorical.py:57-62 stacks the per-sample probabilities sample-major (row s * N + n) and then reshapes the flat
+        log-pmf to (N, S) in C order: the groups that log_predictive's logsumexp runs over mix rows and samples.  Kept as
+        the reference computes it."""
+        N, S = lp.shape
+        return lp.T.reshape(-1).reshape(N, S)
+
     def __init__(self, K, gp_link=None):
         self.K = K
         self.spec = ("Categorical", K)
@@ -154,6 +207,8 @@ class Categorical(_Likelihood):
 
 
 class _TwoParam(_Likelihood):
+    _sample_layout = "NDS"   # (the reference defines no log_predictive for Gamma / Beta; provided on both functions)
+
     def dlogp_df(self, F, y, Y_metadata=None):
         d1 = self._pointwise(F, y)[1]
         return d1[:, 0:1], d1[:, 1:2]

@@ -332,6 +332,20 @@ class SVMOGP(object):
     def _params_now(self):
         return flatten_params(self.q_u_means, self.q_u_chols, self.Z, self.kern_list, self.B_list)
 
+    def _raw_predict(self, Xnew, latent_function_ind=None, full_cov=False, kern=None):
+        """svmogp.py:219-250: q(u_q) at Xnew -- mean K_x^T K_uu^-1 m_q and variance k_xx - K_x^T (K_uu^-1 - K_uu^-1 S_q K_uu^-1) K_x
+        (diagonal only; the reference's full_cov builds the N x N block).  Evaluated as the output function that mixes
+        latent q alone (W = e_q, kappa = 0)."""
+        if full_cov:
+            raise NotImplementedError("full_cov=True builds an N x N matrix; only the marginal variances are provided")
+        q = 0 if latent_function_ind is None else int(latent_function_ind)
+        params = dict(self._params_now())
+        W = np.zeros_like(params["W"])
+        W[0, q] = 1.0
+        params["W"], params["kappa"] = W, np.zeros_like(params["kappa"])
+        m, v = self._eng.predict_f(params, 0, np.asarray(Xnew, dtype=np.float64))
+        return m[:, 0:1].copy(), np.abs(v[:, 0:1])
+
     def _raw_predict_f(self, Xnew, output_function_ind=None, kern_list=None):
         """q(f_d) at Xnew: (mean (N,1), variance (N,1)).  The reference conditions on the N x N posterior of f_d at the
         training inputs (svmogp.py:263-284, O(N^3)); both routes marginalise the same q(U) and agree where the sparse

@@ -177,6 +177,12 @@ int hmogp_get_kuu(hmogp_engine* e, double* Kuu, double* Luu, double* Kuui);
 /* Y [N], Mf/Vf [N,dim_f] -> VE [N], dm/dv [N,dim_f] (any output may be NULL). */
 int hmogp_lik_var_exp(const hmogp_lik_desc* lik, int64_t N, const double* Y, const double* Mf, const double* Vf,
                       double* VE, double* dm, double* dv, int32_t precision, int32_t mem_kind, void* cuda_stream);
+/* predictive(m, v) of likelihoods/<name>.py (e.g. bernoulli.py:113-128, gamma.py:196-238, categorical.py:224-269): mean and
+ * variance of p(y*) under q(f*) = N(Mf, diag Vf), Gauss-Hermite.  Mf/Vf [N,dim_f] -> mean_pred/var_pred [N,dim_p].
+ * gh_tensor: nodes per axis of the tensor grids (Gamma, Beta, Categorical): 10 = an instance that has run var_exp
+ * (a trained model), 20 = a fresh instance (GPy caches the first table it builds). */
+int hmogp_lik_predictive(const hmogp_lik_desc* lik, int64_t N, const double* Mf, const double* Vf, double* mean_pred,
+                         double* var_pred, int32_t gh_tensor, int32_t mem_kind, void* cuda_stream);
 /* logpdf / dlogp_df / d2logp_df2 at given F [N,dim_f]: logp [N], dlogp/d2logp [N,dim_f]. */
 int hmogp_lik_pointwise(const hmogp_lik_desc* lik, int64_t N, const double* F, const double* Y, double* logp,
                         double* dlogp, double* d2logp, int32_t mem_kind, void* cuda_stream);

@@ -91,6 +91,18 @@ def likelihood_golden():
             dm, dv = lik.var_exp_derivatives(Y, M, V)
         out[tag + "_Y"], out[tag + "_M"], out[tag + "_V"] = Y, M, V
         out[tag + "_ve"], out[tag + "_dm"], out[tag + "_dv"] = np.asarray(ve).reshape(n, 1), np.asarray(dm).reshape(n, F), np.asarray(dv).reshape(n, F)
+        # prediction (svmogp.py:340-378): predictive moments on the instance that has already run var_exp (so the cached
+        # Gauss-Hermite table is the training one) and the seeded Monte-Carlo log predictive
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if spec[0] == "Gaussian":
+                pm, pv = lik.predictive(M, V, None)
+            else:
+                pm, pv = lik.predictive(M, V)
+            out[tag + "_pm"], out[tag + "_pv"] = np.asarray(pm).reshape(n, -1), np.asarray(pv).reshape(n, -1)
+            if hasattr(lik, "log_predictive"):
+                np.random.seed(7)
+                out[tag + "_lp"] = np.asarray(lik.log_predictive(Y, M, V, 40)).reshape(1)
         # pointwise at F = M
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")

@@ -326,3 +326,62 @@ def test_svmogp_with_process_group_shards_rows():
     finally:
         if created:
             dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("tag", gu.LIK_TAGS)
+def test_likelihood_predictive_matches_reference_golden(tag):
+    """predictive(m, v) and the seeded Monte-Carlo log_predictive of every likelihood class against the UNMODIFIED reference
+    (fixtures written after var_exp has run on the instance, as in a trained model: SURVEY App. C-3)."""
+    from hetmogp_b200 import likelihoods as L
+    g = gu.load_likelihoods()
+    lik = L.from_spec(gu.LIK_SPECS[tag])
+    Y, M, V = g[tag + "_Y"], g[tag + "_M"], g[tag + "_V"]
+    pm, pv = lik.predictive(M, V)
+    assert pm.shape == g[tag + "_pm"].shape and pv.shape == g[tag + "_pv"].shape
+    assert pu.relerr(pm, g[tag + "_pm"]) < 1e-10
+    if np.any(g[tag + "_pv"]):
+        assert pu.relerr(pv, g[tag + "_pv"]) < 1e-9
+    else:
+        assert not np.any(pv)                                               # Categorical: variance "NOT IMPLEMENTED" -> zeros
+    if tag + "_lp" in g:
+        np.random.seed(7)
+        lp = lik.log_predictive(Y, M, V, 40)
+        assert abs(lp - g[tag + "_lp"][0]) < 1e-9 * max(1.0, abs(g[tag + "_lp"][0]))
+
+
+def test_model_prediction_entry_points():
+    """svmogp.py:219-378 on the O(M^2) route: _raw_predict (latent u_q), _raw_predict_f / predictive_new (output function d),
+    predictive (likelihood moments) and negative_log_predictive, against the oracle's posterior moments at the same inputs."""
+    prob, g = gu.load_case("cfg1_toy")
+    m, meta = real_model(prob)
+    o = diag_oracle.elbo_and_grads(prob, want_rows=True)
+    fi, di = meta['function_index'].flatten(), meta['d_index'].flatten()
+    for d in range(prob["J"]):
+        mu, var = m._raw_predict_f(prob["X"][fi[d]], output_function_ind=d)
+        assert mu.shape == (prob["X"][fi[d]].shape[0], 1)
+        assert pu.relerr(mu, g["m_fd_%d" % d]) < 1e-7 and pu.relerr(var, g["v_fd_%d" % d]) < 1e-7
+    mu2, var2 = m.predictive_new(prob["X"][0][:7], output_function_ind=1)
+    assert pu.relerr(mu2, g["m_fd_1"][:7]) < 1e-7
+    # latent q: mean K_x^T K_uu^-1 m_q, variance sigma^2 - K_x^T (K_uu^-1 - K_uu^-1 S K_uu^-1) K_x  (numpy, fp64)
+    Xn = np.linspace(0.05, 0.95, 9)[:, None]
+    for q in range(prob["Q"]):
+        z = prob["Z"][:, q:q + 1]
+        Kuu, _ = diag_oracle.rbf_K(z, z, prob["rbf_var"][q], prob["rbf_ls"][q], same=True)
+        Kx, _ = diag_oracle.rbf_K(z, Xn, prob["rbf_var"][q], prob["rbf_ls"][q])
+        Ki = np.linalg.inv(Kuu)
+        Lq = diag_oracle.unpack_lower(prob["L_u"][:, q], prob["M"])
+        mu_ref = Kx.T.dot(Ki.dot(prob["m_u"][:, q]))
+        var_ref = prob["rbf_var"][q] - np.sum(Kx * (Ki - Ki.dot(Lq.dot(Lq.T)).dot(Ki)).dot(Kx), 0)
+        mu, var = m._raw_predict(Xn, latent_function_ind=q)
+        assert pu.relerr(mu[:, 0], mu_ref) < 1e-8 and pu.relerr(var[:, 0], np.abs(var_ref)) < 1e-8
+    # likelihood-level prediction = the likelihood's predictive on the oracle's moments
+    mp, vp = m.predictive(prob["X"])
+    for t, lik in enumerate(m.likelihood.likelihoods_list):
+        rm, rv = lik.predictive(o["rows"]["m"][t], np.abs(o["rows"]["v"][t]))
+        assert pu.relerr(mp[t], rm) < 1e-7
+    np.random.seed(3)
+    nlpd = m.negative_log_predictive(prob["X"], prob["Y"], num_samples=30)
+    np.random.seed(3)
+    ref = -sum(lik.log_predictive(prob["Y"][t], o["rows"]["m"][t], np.abs(o["rows"]["v"][t]), 30)
+               for t, lik in enumerate(m.likelihood.likelihoods_list))
+    assert np.isfinite(nlpd) and abs(nlpd - ref) < 1e-6 * abs(ref)
