@@ -422,7 +422,7 @@ def main():
     # (kernel name, algorithmic flops per launch, launches per step) of the N-sized kernels behind each phase timer
     if prec == "tc":
         kern = {"forward_ms": ("tc_fwd_kernel (K_fu build + K_fu C_q on tcgen05 cta_group::2 + row reductions)", work["flops_fwd"], 1),
-                "bwd_gram_ms": ("tc_gram2_kernel (H^1 = K_fu^T diag(omega) K_fu on tcgen05 cta_group::2, three-level accumulation)", work["flops_gram"], 1)}
+                "bwd_gram_ms": ("tc_gram2_kernel (H^1 = K_fu^T diag(omega) K_fu on tcgen05 cta_group::2, two alternating TMEM accumulators folded into fp64)", work["flops_gram"], 1)}
         if args.what == "full":
             kern["bwd_proj_ms"] = ("tc_bwd_kernel (transposed projection C_q K_fu^T on tcgen05 cta_group::2 + column sums)", work["flops_bwd_proj"], 1)
     else:
@@ -433,13 +433,15 @@ def main():
     dom = max(kern, key=lambda k: per_launch[k])
     ach = kern[dom][1] / (per_launch[dom] * 1e-3) / 1e12 if per_launch[dom] > 0 else 0.0
     n_kernel_ms = sum(med.get(k, 0.0) for k in kern)
-    tinfo = eng.tc_info() if (prec == "tc" and hasattr(eng, "tc_info")) else {}
-    Mc = tinfo.get("Mc", -(-M // 256) * 256)
-    passes = tinfo.get("passes", {"forward_ms": 3, "bwd_proj_ms": 3, "bwd_gram_ms": 3})
-    gram_frac = tinfo.get("gram_block_fraction", 0.75 if Mc % 256 == 0 else 0.625)
-    issued = {"forward_ms": passes["forward_ms"] * 2.0 * work["U"] / (M * M) * Mc * Mc,           # MMA products issued, padded M
-              "bwd_proj_ms": passes["bwd_proj_ms"] * 2.0 * work["U"] / (M * M) * Mc * Mc,
-              "bwd_gram_ms": passes["bwd_gram_ms"] * 2.0 * work["U"] / (M * M) * (Mc * Mc) * gram_frac}
+    # MMA products actually issued (padded M; split-fp16: 3 products per algorithmic one, 2 on the Gram's diagonal blocks;
+    # the Gram computes the lower triangle in 256 x 256 blocks)
+    Mc = -(-M // 256) * 256
+    nb = Mc // 256
+    gram_blocks = 3.0 * (nb * (nb - 1) // 2) + 2.0 * nb
+    passes = {"forward_ms": 3.0, "bwd_proj_ms": 3.0, "bwd_gram_ms": gram_blocks / (nb * (nb + 1) // 2)}
+    issued = {"forward_ms": 3.0 * 2.0 * work["U"] / (M * M) * Mc * Mc,
+              "bwd_proj_ms": 3.0 * 2.0 * work["U"] / (M * M) * Mc * Mc,
+              "bwd_gram_ms": 2.0 * work["U"] / (M * M) * 256 * 256 * gram_blocks}
     traffic_ncu = {"bwd_gram_ms": 3.11e8, "forward_ms": 3.08e8, "bwd_proj_ms": 4.97e8}
     headline = prec == "tc" and args.config == "cfg3" and world == 1 and not args.rows
     roofline = {"bound": "tensor", "kernel": kern[dom][0], "achieved": ach, "peak": peaks["tc"], "unit": "TFLOP/s",

@@ -6,22 +6,37 @@
 // /root/reference/hetmogp/svmogp_inf.py:145-148, summed over d with W_dq^2 folded into omega) and
 // dVE/dm_q (svmogp_inf.py:144).
 //
-// Same accumulation scheme as tc_gram.cu (TMEM level 1 -> TMEM level 2 -> fp64 partial tiles), different operand
-// economy.  The weight is split symmetrically: with V[n, m] = 2^kexp K[n,m] sqrt|omega_n| 2^se (K 2^kexp < 2^12, sqrt|omega| 2^se <= 4),
+// Operand economy.  The weight is split symmetrically: with V[n, m] = 2^kexp K[n,m] sqrt|omega_n| 2^se (K 2^kexp < 2^12,
+// sqrt|omega| 2^se <= 4),
 //     H = 2^-(2 kexp + 2 se) (sgn(omega) V)^T V,
-// so both operands come from ONE generated and split value.  When all weights of a 64-row chunk have the same sign (the
-// usual case: omega <= 0 for log-concave likelihoods) the MMA applies the sign through the negate-A bit of its instruction
-// descriptor, and on a diagonal block the A descriptor simply points at the B tile; in a mixed-sign chunk the A operand is
-// the B operand with the sign bit of the row flipped (an XOR on the packed fp16 pairs).  A CTA pair owns a 256 x 256 output block: CTA r generates its 128 rows of
-// A and its 128-column half of B per 64-row chunk (cta_group::2 takes the other half from the peer's shared memory), so
-// a 128 x 256 MMA tile costs 256 generated columns off the diagonal and 128 on it, against 384 in the one-CTA kernel.
+// so both operands come from ONE generated and split value (V = Vh + Vl in fp16).  When all weights of a 64-row chunk have
+// the same sign (the usual case: omega <= 0 for log-concave likelihoods) the MMA applies the sign through the negate-A bit
+// of its instruction descriptor, and on a diagonal block the A descriptor simply points at the B tile; in a mixed-sign
+// chunk the A operand is the B operand with the sign bit of the row flipped (an XOR on the packed fp16 pairs).  A CTA pair
+// owns a 256 x 256 output block: CTA r generates its 128 rows of A and its 128-column half of B per 64-row chunk
+// (cta_group::2 takes the other half from the peer's shared memory), so a 128 x 256 MMA tile costs 256 generated columns
+// off the diagonal and 128 on it, against 384 in the one-CTA kernel.  Off the diagonal a stage takes three products
+// (Vh^T Vh + Vh^T Vl + Vl^T Vh); on it two: Y = Vh^T Vh + Vh^T (2 Vl), whose symmetric part is the same sum -- the reduce
+// kernel symmetrises diagonal blocks (HM_G2_SYMDIAG).
+//
+// Accumulation.  tcgen05 adds into its fp32 accumulator with truncation, so a long accumulation drifts by a bias that grows
+// with the window length and is then amplified by K_uu^-1 . K_uu^-1 in the finish chain ("Gram accuracy").  The
+// 512 TMEM columns therefore hold TWO 128 x 256 accumulators; windows of `f1` chunks alternate between them.  While the
+// MMA issuer fills one, four fold warps (one per TMEM lane quadrant) drain the other: tcgen05.ld -> fp64 add into this
+// CTA's partial tile in L2 (slot_index: every warp-wide access is 32 consecutive 16-byte pieces) -> write
+// -HM_G2_CARRY x value back as the start of that buffer's next window.  The carry keeps the accumulator centred around
+// zero, where truncation errors of growing and shrinking magnitudes cancel to first order; the bookkeeping is exact:
+// sum_w S_w = sum_w (1 + carry_w) v_w, with carry_w = HM_G2_CARRY when the buffer has another window in the segment, else 0,
+// which is what the fold adds.  Generators never stop for a fold; a fold has one window's time to finish.  The fold is
+// bound by L2 bandwidth (512 KB of read-modify-write per CTA and window: 3.6 TB/s over the chip at 1024-row windows), not
+// by latency: a software-pipelined loop with the tile pieces requested two steps ahead measured slower (13.4 vs 12.6 ms).
 //
 // MMA: D[i (2 x 128 TMEM lanes), j (256 columns)] += A[i][n] . B[j][n]^T over n = 64 data rows per stage (SWIZZLE_128B).
-// Warp roles (640 threads per CTA, one CTA per SM, pairs persistent over a host-built plan of segments):
-//   warps 0-15  generators: (column group of 32) x (16 of the 64 rows); all 16 also run the level-2/3 folds (their
-//               16-deep tcgen05.ld parallelism is what keeps a fold at the TMEM read rate)
+// Warp roles (768 threads per CTA at 80 registers, one CTA per SM, pairs persistent over a host-built plan of segments):
+//   warps 0-15  generators: (column group of 32) x (16 of the 64 rows)
 //   warp 16     leader: MMA issuer (one thread); peer: relays "my stage is written" to the leader's barrier
 //   warps 17-19 row loaders (x, sqrt|omega|, sign words, mu -> smem ring), alternating groups of 2 chunks
+//   warps 20-23 fold warps (above)
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -44,7 +59,7 @@ namespace {
 #define HM_G2_SYMDIAG 1   // diagonal blocks: Y = Vh^T Vh + Vh^T (2 Vl), symmetrised by the reduce kernel (2 products instead of 3)
 #endif
 #ifndef HM_G2_CENTRE
-#define HM_G2_CENTRE 1    // level-1 windows start at minus half the expected window sum (truncation bias cancels)
+#define HM_G2_CENTRE 1    // carry-centred windows (header comment)
 #endif
 constexpr int kC = HM_GRAM2_CHUNK;                 // data rows per chunk = MMA K extent per stage (4 x K16)
 constexpr int kStages = 3;
