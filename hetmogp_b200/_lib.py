@@ -99,6 +99,8 @@ def _load():
         "hmogp_lik_predictive": (C.c_int, [C.POINTER(LikDesc), i64, vp, vp, vp, vp, i32, i32, vp]),
         "hmogp_flat_to_triang": (C.c_int, [vp, vp, i32, i32, i32, vp]),
         "hmogp_triang_to_flat": (C.c_int, [vp, vp, i32, i32, i32, vp]),
+        "hmogp_hint_hyper_unchanged": (C.c_int, [vp, i32]),
+        "hmogp_kuu_reuse_count": (C.c_int64, [vp]),
         "hmogp_enable_timing": (C.c_int, [vp, i32]),
         "hmogp_last_timing": (C.c_int, [vp, C.POINTER(C.c_float), c_int32_p]),
         "hmogp_tc_built": (C.c_int, []),

@@ -419,7 +419,13 @@ struct hmogp_engine {
     //   prepA: padding, S / S^-1 branch (forked), K_uu build and Cholesky -> host checks the pivot flags (jitchol)
     //   prepB: K_uu^-1, alpha, S K^-1, K^-1 S K^-1, C, KL, tensor-core operand image
     //   fin[k]: the finish chain for one (statistics buffer, what, dL_dKmm wanted) combination
-    cudaGraphExec_t prepA_graph, prepB_graph;
+    cudaGraphExec_t prepA_graph, prepB_graph, prepR_graph;   // R: the chain with K_uu's factorisation reused
+    long long prepR_launches;
+    // K_uu, its Cholesky factor, the inverses: valid for the (Z, sigma^2, l) in kuu_key_h (host callers) or, for device
+    // callers, on the caller's word (hmogp_hint_hyper_unchanged)
+    bool kuu_valid, kuu_key_ok, hint_unchanged, kuu_cache_off;
+    std::vector<double> kuu_key_h;
+    long long kuu_reused;
     long long prepA_launches, prepB_launches;
     struct FinGraph { cudaGraphExec_t exec; const double* stats; int what; bool dkmm; long long launches; };
     std::vector<FinGraph> fin_graphs;
@@ -544,7 +550,7 @@ static int dbg_skip() { static int v = -1; if (v < 0) { const char* e = getenv("
 // part A on streams (s, s2): padded inputs; S = Lu Lu^T, Lu^-1, S^-1 on the side stream; K_uu (with the jitter in
 // e->jitter_d), its copy into Luu, cleared flags, blocked Cholesky.  `graphed_chol`: replay the Cholesky's own graph
 // (direct issue; inside a capture the launches are recorded individually).
-int prepare_partA(hmogp_engine* e, cudaStream_t s, cudaStream_t s2, bool graphed_chol) {
+int prepare_partA(hmogp_engine* e, cudaStream_t s, cudaStream_t s2, bool graphed_chol, bool reuse = false) {
     const int M = e->M, Mp = e->Mp, Q = e->Q, Xd = e->Xd;
     const int64_t sQ = (int64_t)Mp * Mp;
     {
@@ -560,24 +566,29 @@ int prepare_partA(hmogp_engine* e, cudaStream_t s, cudaStream_t s2, bool graphed
     if (!HM_SKIP(4)) HM_CHECK(hm_tri_inverse(s2, e->Lu, e->LuInv, e->T1, Mp, sQ, Q));
     HM_CHECK(hm_dgemm(s2, true, false, Mp, Mp, Mp, 1.0, e->LuInv, Mp, sQ, e->LuInv, Mp, sQ, 0.0, e->Sinv, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR | HM_GEMM_K_GE));
     HM_CUDA(cudaEventRecord(e->ev_Sinv, s2));
-    // K_uu, Cholesky (util.py:197-198)
-    HM_CHECK(hm_build_kuu(s, e->Zp, e->consts, e->jitter_d, e->Kuu, M, Mp, Xd, Q));
-    HM_CUDA(cudaMemcpyAsync(e->Luu, e->Kuu, sizeof(double) * sQ * Q, cudaMemcpyDeviceToDevice, s));
+    // K_uu, Cholesky (util.py:197-198); `reuse`: Z, sigma^2, l are those of the resident factorisation (VE phases of VEM,
+    // svmogp.py:104-113 with the hyper-parameters fixed: only m_u and L_u move)
     HM_CUDA(cudaMemsetAsync(e->flags_d, 0, sizeof(int) * 2 * HM_MAXQ, s));
-    if (!HM_SKIP(1)) {
-        if (graphed_chol) HM_CHECK(cholesky_graphed(e));
-        else HM_CHECK(hm_cholesky(s, e->Luu, Mp, sQ, Q, e->flags_d));
+    if (!reuse) {
+        HM_CHECK(hm_build_kuu(s, e->Zp, e->consts, e->jitter_d, e->Kuu, M, Mp, Xd, Q));
+        HM_CUDA(cudaMemcpyAsync(e->Luu, e->Kuu, sizeof(double) * sQ * Q, cudaMemcpyDeviceToDevice, s));
+        if (!HM_SKIP(1)) {
+            if (graphed_chol) HM_CHECK(cholesky_graphed(e));
+            else HM_CHECK(hm_cholesky(s, e->Luu, Mp, sQ, Q, e->flags_d));
+        }
     }
     HM_CUDA(cudaStreamWaitEvent(s, e->ev_Sinv, 0));   // join (a captured graph must not leave the side stream dangling)
     return 0;
 }
 
 // part B on stream s: K_uu^-1 = Luu^-T Luu^-1 (dpotri, util.py:199), alpha, S K^-1, K^-1 S K^-1, C, KL, operand image
-int prepare_partB(hmogp_engine* e, cudaStream_t s) {
+int prepare_partB(hmogp_engine* e, cudaStream_t s, bool reuse = false) {
     const int M = e->M, Mp = e->Mp, Q = e->Q;
     const int64_t sQ = (int64_t)Mp * Mp;
-    if (!HM_SKIP(2)) HM_CHECK(hm_tri_inverse(s, e->Luu, e->LuuInv, e->tmp, Mp, sQ, Q));
-    HM_CHECK(hm_dgemm(s, true, false, Mp, Mp, Mp, 1.0, e->LuuInv, Mp, sQ, e->LuuInv, Mp, sQ, 0.0, e->Ki, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR | HM_GEMM_K_GE));
+    if (!reuse) {
+        if (!HM_SKIP(2)) HM_CHECK(hm_tri_inverse(s, e->Luu, e->LuuInv, e->tmp, Mp, sQ, Q));
+        HM_CHECK(hm_dgemm(s, true, false, Mp, Mp, Mp, 1.0, e->LuuInv, Mp, sQ, e->LuuInv, Mp, sQ, 0.0, e->Ki, Mp, sQ, Q, 1, 0, 0, 0, HM_GEMM_MIRROR | HM_GEMM_K_GE));
+    }
     {
         dim3 grid((unsigned)hm_cdiv(Mp, 8), (unsigned)Q);
         dgemv_kernel<<<grid, 256, 0, s>>>(e->Ki, e->mp, e->alpha, Mp);
@@ -655,6 +666,49 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
 #endif
     ++e->prepare_calls;
     for (int q = 0; q < Q; ++q) { e->jitter_h[q] = 0.0; e->chol_fail_h[q] = 0; }
+    // ---- is the resident factorisation of K_uu the one these parameters need?  Host callers: compared bit by bit with
+    // the values it was built from; device callers: only on their explicit word for this call.
+    bool reuse = false;
+    {
+        const size_t nz = (size_t)M * Q * Xd, nk = nz + 2 * (size_t)Q;
+        if (mem_kind == HMOGP_MEM_HOST) {
+            if (e->kuu_key_h.size() != nk) { e->kuu_key_h.assign(nk, 0.0); e->kuu_key_ok = false; }
+            const bool same = e->kuu_key_ok && memcmp(e->kuu_key_h.data(), p->Z, sizeof(double) * nz) == 0 &&
+                              memcmp(e->kuu_key_h.data() + nz, p->rbf_var, sizeof(double) * Q) == 0 &&
+                              memcmp(e->kuu_key_h.data() + nz + Q, p->rbf_ls, sizeof(double) * Q) == 0;
+            reuse = same && e->kuu_valid;
+            if (!same) {
+                memcpy(e->kuu_key_h.data(), p->Z, sizeof(double) * nz);
+                memcpy(e->kuu_key_h.data() + nz, p->rbf_var, sizeof(double) * Q);
+                memcpy(e->kuu_key_h.data() + nz + Q, p->rbf_ls, sizeof(double) * Q);
+                e->kuu_key_ok = true;
+            }
+        } else {
+            reuse = e->kuu_valid && e->hint_unchanged;
+            if (!reuse) e->kuu_key_ok = false;      // the key no longer describes what is resident
+        }
+        e->hint_unchanged = false;
+#ifdef HM_DEBUG_SKIP
+        reuse = false;
+#endif
+        if (e->kuu_cache_off) reuse = false;
+    }
+    if (reuse) {
+        ++e->kuu_reused;
+        if (graphs) {
+            if (!e->prepR_graph) HM_CHECK(capture_graph(e, &e->prepR_graph, &e->prepR_launches, [&](cudaStream_t cs) {
+                const int rc = prepare_partA(e, cs, e->s2, false, true);
+                return rc ? rc : prepare_partB(e, cs, true);
+            }));
+            HM_CUDA(cudaGraphLaunch(e->prepR_graph, s));
+            hm_launch_counter += e->prepR_launches - 1;
+        } else {
+            HM_CHECK(prepare_partA(e, s, e->s2, false, true));
+            HM_CHECK(prepare_partB(e, s, true));
+        }
+        return 0;
+    }
+    e->kuu_valid = false;
     HM_CUDA(cudaMemsetAsync(e->jitter_d, 0, sizeof(double) * HM_MAXQ, s));
     if (graphs) {
         if (!e->prepA_graph) HM_CHECK(capture_graph(e, &e->prepA_graph, &e->prepA_launches, [&](cudaStream_t cs) { return prepare_partA(e, cs, e->s2, false); }));
@@ -696,6 +750,9 @@ int mm_prepare(hmogp_engine* e, const hmogp_params* p, int mem_kind) {
         HM_CUDA(cudaGraphLaunch(e->prepB_graph, s));
         hm_launch_counter += e->prepB_launches - 1;
     } else HM_CHECK(prepare_partB(e, s));
+    // a factorisation that needed jitter is not kept: the retry ladder is part of the call's reported status
+    e->kuu_valid = true;
+    for (int q = 0; q < Q; ++q) if (e->jitter_h[q] != 0.0) e->kuu_valid = false;
     return 0;
 }
 
@@ -1015,7 +1072,9 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
     e->s2 = nullptr; e->ev_fork = e->ev_S = e->ev_Sinv = nullptr;
     e->sc = nullptr; e->ev_cfence = e->ev_data = e->ev_dataY = nullptr; e->data_pending = e->dataY_pending = false;
     e->chol_graph = nullptr;
-    e->prepA_graph = e->prepB_graph = nullptr; e->prepA_launches = e->prepB_launches = 0; e->prepare_calls = 0;
+    e->prepA_graph = e->prepB_graph = e->prepR_graph = nullptr; e->prepA_launches = e->prepB_launches = e->prepR_launches = 0; e->prepare_calls = 0;
+    e->kuu_valid = e->kuu_key_ok = e->hint_unchanged = false; e->kuu_reused = 0;
+    { const char* v = getenv("HMOGP_NO_KUU_CACHE"); e->kuu_cache_off = v && atoi(v) != 0; }
     { const char* v = getenv("HMOGP_NO_GRAPH"); e->graphs_off = v && atoi(v) != 0; }
     for (int t = 0; t < HM_MAXT; ++t) e->up_X[t] = e->up_Y[t] = nullptr;
     if (!rc && (cudaStreamCreateWithFlags(&e->s2, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1052,6 +1111,7 @@ void hmogp_destroy(hmogp_engine* e) {
     if (e->chol_graph) cudaGraphExecDestroy(e->chol_graph);
     if (e->prepA_graph) cudaGraphExecDestroy(e->prepA_graph);
     if (e->prepB_graph) cudaGraphExecDestroy(e->prepB_graph);
+    if (e->prepR_graph) cudaGraphExecDestroy(e->prepR_graph);
     for (auto& f : e->fin_graphs) if (f.exec) cudaGraphExecDestroy(f.exec);
     if (e->ev_cfence) cudaEventDestroy(e->ev_cfence);
     if (e->ev_data) cudaEventDestroy(e->ev_data);
@@ -1563,6 +1623,14 @@ int hmogp_triang_to_flat(const double* dense, double* flat, int32_t M, int32_t D
     int rc2 = staged_finish(mem_kind, s, ins, outs, din, dout);
     return rc ? rc : rc2;
 }
+
+int hmogp_hint_hyper_unchanged(hmogp_engine* e, int32_t unchanged) {
+    if (!e) { hm_set_error("null engine"); return HMOGP_ERR_ARG; }
+    e->hint_unchanged = unchanged != 0;
+    return 0;
+}
+
+int64_t hmogp_kuu_reuse_count(hmogp_engine* e) { return e ? (int64_t)e->kuu_reused : -1; }
 
 int hmogp_enable_timing(hmogp_engine* e, int32_t on) {
     if (!e) { hm_set_error("null engine"); return HMOGP_ERR_ARG; }

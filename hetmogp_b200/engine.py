@@ -142,12 +142,15 @@ class Engine(object):
             setattr(gs, k, ptr(a))
         return out, gs
 
-    def evaluate(self, params, what="full", want_dKmm=False, out=None):
+    def evaluate(self, params, what="full", want_dKmm=False, out=None, hyper_unchanged=False):
         """params: dict with Z, m_u, L_u, rbf_var, rbf_ls, W, kappa [, W_chain, kappa_chain, batch_scale] as numpy
         arrays (host path: copies inside the call) or torch CUDA tensors (device path).  Returns a dict of outputs
         in the reference's layouts (see include/hetmogp_b200.h); ``self.status`` holds the flags.  With host parameters the
         returned numpy arrays are backed by pooled page-locked buffers that stay theirs for as long as they are referenced
-        (no aliasing between calls)."""
+        (no aliasing between calls).  The factorisation of K_uu is reused between calls whose Z / rbf_var / rbf_ls are
+        bitwise equal (host parameters: detected; CUDA-tensor parameters: only with ``hyper_unchanged=True``)."""
+        if hyper_unchanged:
+            check(lib.hmogp_hint_hyper_unchanged(self._h, 1))
         w = {"elbo": _lib.WHAT_ELBO, "ve": _lib.WHAT_VE, "full": _lib.WHAT_FULL}[what] if isinstance(what, str) else what
         on_device = hasattr(params["m_u"], "data_ptr")
         kind = _lib.MEM_DEVICE if on_device else _lib.MEM_HOST
@@ -180,6 +183,10 @@ class Engine(object):
         if self.status["n_negative_v"] > 0:
             print('v negative!')   # svmogp_inf.py:221-222 (warning only)
         return out
+
+    @property
+    def kuu_reuse_count(self):
+        return int(lib.hmogp_kuu_reuse_count(self._h))
 
     def predict_f(self, params, t, Xnew):
         """q(f_d) at new inputs for the output functions of task t: (m_fd, v_fd), each (N, dim_f[t]) -- the forward

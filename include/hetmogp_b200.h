@@ -224,6 +224,16 @@ int hmogp_opt_lookahead(hmogp_opt* o, int32_t apply_momentum, void* cuda_stream)
 /* g = -transformed gradient (zero where gated off), then the Adadelta update; grad_out [n] receives g (or NULL) */
 int hmogp_opt_update(hmogp_opt* o, int32_t ve_active, int32_t vm_active, double* grad_out, void* cuda_stream);
 
+/* K_uu, its Cholesky factor and the two inverses (util.latent_funs_cov, util.py:181-200) stay resident between
+ * evaluations and are reused when Z, rbf_var and rbf_ls are bitwise those they were built from: the VE phases of VEM
+ * (svmogp.py:104-113 with the hyper-parameters fixed, util.py:284-331) only move m_u and L_u.  With HMOGP_MEM_HOST
+ * parameters the engine compares the values itself; with HMOGP_MEM_DEVICE parameters it cannot see them, and reuses the
+ * factorisation for the NEXT evaluation only if the caller says so here.  A factorisation that needed jitter is never
+ * reused.  hmogp_kuu_reuse_count: evaluations of this engine that reused it (test / diagnostic).  HMOGP_NO_KUU_CACHE=1
+ * in the environment turns the reuse off. */
+int hmogp_hint_hyper_unchanged(hmogp_engine* e, int32_t unchanged);
+int64_t hmogp_kuu_reuse_count(hmogp_engine* e);
+
 /* ---- timing hooks for bench.py: CUDA-event time (ms) and launch count of the N-sized kernels of the
  *      last evaluation, measured on the engine's stream. ---- */
 int hmogp_enable_timing(hmogp_engine* e, int32_t on);

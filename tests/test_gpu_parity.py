@@ -172,6 +172,55 @@ def test_benchmark_shape_against_oracle():
             assert v < 3e-2, (k, v)         # v = k_nn + c_n cancels on well-determined rows (forward fp32-format floor)
 
 
+def test_kuu_factorisation_is_reused_only_for_unchanged_hyperparameters():
+    """The resident K_uu / Cholesky / inverse are reused when Z, rbf_var, rbf_ls are bitwise unchanged (VE phases of VEM) and
+    the results are bit-identical to a fresh engine's; any change of a hyper-parameter recomputes them; CUDA-tensor
+    parameters reuse only on the caller's word."""
+    import torch
+    c = dict(CASES["pad_m300"])
+    prob = synth.make_problem(c.pop("liks"), c.pop("N"), c.pop("M"), c.pop("Q"), Xdim=c.pop("Xdim"), seed=7, **c)
+    keys = ("log_marginal", "dL_dmu_u", "dL_dL_u", "dL_dKmm", "d_rbf", "dW", "dkappa", "dZ")
+
+    def fresh(p, prec):
+        e = pu.make_engine(prob, prec)
+        o = {k: np.array(v) for k, v in e.evaluate(p, what="full", want_dKmm=True).items()}
+        e.close()
+        return o
+
+    for prec in ("fp64", "tc"):
+        p1 = pu.params_of(prob)
+        eng = pu.make_engine(prob, prec)
+        eng.evaluate(p1, what="full", want_dKmm=True)
+        assert eng.kuu_reuse_count == 0
+        p2 = dict(p1)
+        p2["m_u"] = p1["m_u"] + 0.01
+        p2["L_u"] = p1["L_u"] * 1.01
+        for n in (1, 2, 3):                        # direct issue, then graph replays
+            out = eng.evaluate(p2, what="full", want_dKmm=True)
+            assert eng.kuu_reuse_count == n
+        ref = fresh(p2, prec)
+        for k in keys:
+            assert np.array_equal(out[k], ref[k]), (prec, k)
+        p3 = dict(p2)
+        p3["rbf_ls"] = p2["rbf_ls"] * (1.0 + 1e-15) + 1e-16
+        assert not np.array_equal(p3["rbf_ls"], p2["rbf_ls"])
+        out = eng.evaluate(p3, what="full", want_dKmm=True)
+        assert eng.kuu_reuse_count == 3
+        ref = fresh(p3, prec)
+        for k in keys:
+            assert np.array_equal(out[k], ref[k]), (prec, k)
+        pd = {k: torch.as_tensor(np.ascontiguousarray(v), device="cuda") for k, v in p3.items() if v is not None}
+        out = eng.evaluate(pd, what="full", want_dKmm=True)
+        assert eng.kuu_reuse_count == 3            # device parameters: not without the hint
+        out = eng.evaluate(pd, what="full", want_dKmm=True, hyper_unchanged=True)
+        assert eng.kuu_reuse_count == 4
+        for k in keys:
+            assert np.array_equal(out[k].cpu().numpy(), ref[k]), (prec, k)
+        out = eng.evaluate(pd, what="full", want_dKmm=True)      # the hint holds for one call
+        assert eng.kuu_reuse_count == 4
+        eng.close()
+
+
 def test_single_cta_kernel_variants(monkeypatch):
     """The one-CTA forward (HMOGP_TC_FWD_CTAS=1) and the one-CTA Gram kernel (HMOGP_TC_GRAM_CTAS=1, tc_gram.cu) stay
     selectable and correct: same oracle case as the default CTA-pair kernels."""
