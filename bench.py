@@ -257,6 +257,7 @@ def main():
     what_id = {"elbo": 0, "ve": 1, "full": 2}[args.what]
 
     # ---------------------------------------------------------------- resident arm ("value")
+    Engine.print_v_negative = False     # stdout carries ONE JSON line; negative-variance rows are counted in "status"
     eng = Engine(prob["lik_specs"], M, Q, Xdim, precision=prec, device=local, group=group)
     stream = torch.cuda.current_stream(dev).cuda_stream
     eng.set_stream(stream)
@@ -338,6 +339,7 @@ def main():
     ms_step, phases, wall = timed(resident_step, args.steps, max(3, args.warmup), sampler, eng)
     clocks = sampler.stop() if sampler else None
     elbo_resident = float(out_dev["log_marginal"].cpu()[0, 0])
+    status_resident = dict(eng.status) if eng.status else None
     launches = int(np.sum([p["launches"] for p in phases])) + (2 * args.steps if opt is not None else 0)
 
     # side measurements on the same resident data: evaluation only, VE step, ELBO only (SURVEY 8d asks for them)
@@ -451,7 +453,7 @@ def main():
     issued = {"forward_ms": 3.0 * 2.0 * work["U"] / (M * M) * Mc * Mc,
               "bwd_proj_ms": 3.0 * 2.0 * work["U"] / (M * M) * Mc * Mc,
               "bwd_gram_ms": 2.0 * work["U"] / (M * M) * 256 * 256 * gram_blocks}
-    traffic_ncu = {"bwd_gram_ms": 3.11e8, "forward_ms": 3.08e8, "bwd_proj_ms": 4.97e8}
+    traffic_ncu = {"bwd_gram_ms": 3.48e8, "forward_ms": 3.11e8, "bwd_proj_ms": 4.93e8}   # profiles/r2_ncu_summary.txt
     headline = prec == "tc" and args.config == "cfg3" and world == 1 and not args.rows
     roofline = {"bound": "tensor", "kernel": kern[dom][0], "achieved": ach, "peak": peaks["tc"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tc"],
@@ -481,7 +483,7 @@ def main():
     line = {"metric": "ELBO steps/sec (ELBO + all gradients)", "value": 1e3 / ms_step, "unit": "ELBO steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": {"tc": "f16x2 split (fp16 hi/lo on tcgen05, fp32 accumulate; fp64 M x M algebra)", "fp32": "f32", "fp64": "f64"}[prec],
-            "data": "synthetic", "config": workload_config(args, c), "elbo": elbo_resident, "clocks": clocks,
+            "data": "synthetic", "config": workload_config(args, c), "elbo": elbo_resident, "status": status_resident, "clocks": clocks,
             "gpu_launches": launches, "optimizer": None if opt is None else {"kind": "Adadelta (climin semantics), device-resident", "flat_size": n_opt, "step_rate": OPT_STEP_RATE},
             "e2e": e2e, "e2e_pageable": e2e_pageable, "variants": variants, "parity": parity,
             "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": wall}

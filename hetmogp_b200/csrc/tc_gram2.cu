@@ -27,9 +27,10 @@
 // -HM_G2_CARRY x value back as the start of that buffer's next window.  The carry keeps the accumulator centred around
 // zero, where truncation errors of growing and shrinking magnitudes cancel to first order; the bookkeeping is exact:
 // sum_w S_w = sum_w (1 + carry_w) v_w, with carry_w = HM_G2_CARRY when the buffer has another window in the segment, else 0,
-// which is what the fold adds.  Generators never stop for a fold; a fold has one window's time to finish.  The fold is
-// bound by L2 bandwidth (512 KB of read-modify-write per CTA and window: 3.6 TB/s over the chip at 1024-row windows), not
-// by latency: a software-pipelined loop with the tile pieces requested two steps ahead measured slower (13.4 vs 12.6 ms).
+// which is what the fold adds.  Generators never stop for a fold; a fold has one window's time to finish.  What a fold
+// costs is its fp64 accumulation traffic through the L2 (512 KB of read-modify-write per CTA and window; the chip sustains
+// ~3.5 TB/s of it): with the adds taken out the kernel runs at the generator-bound 11 ms down to 256-row windows, and
+// cp.reduce.async.bulk .add.f64 from a staging ring (adds at the L2, nothing read back) costs the same.
 //
 // MMA: D[i (2 x 128 TMEM lanes), j (256 columns)] += A[i][n] . B[j][n]^T over n = 64 data rows per stage (SWIZZLE_128B).
 // Warp roles (768 threads per CTA at 80 registers, one CTA per SM, pairs persistent over a host-built plan of segments):

@@ -1,0 +1,3 @@
+set -x
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
+for v in 1024 512 256 2048 128; do echo "== HMOGP_TC_FLUSH_ROWS=$v"; env HMOGP_TC_FLUSH_ROWS=$v timeout 300 python tools/tc_check.py scale cfg3 1000000 2>&1 | grep -E "TIME cfg3 N=[0-9]* tc (full)|PARITY cfg3 N=1000000 tc vs" | cut -c1-400; done
