@@ -184,6 +184,29 @@ tc_bwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
         const int et = (int)threadIdx.x - kGenWarps * 32;                  // 0..255: row of the super-tile this thread stages
         const float inv_pc = pow2i(-(kexp + cexp));
         uint32_t jc = 0, scount = 0;
+        // The row this thread stages for the NEXT super-tile is fetched from HBM while the current one is processed: the
+        // round trip (~1 us) used to sit between two named barriers at the head of every super-tile's epilogue, on the path
+        // that decides when the MMAs get their accumulator buffer back.
+        double x_n[XD];
+        float mc_n = 0.f, oc_n = 0.f, mu_n = 0.f;
+        auto fetch_row = [&](int64_t st) {
+#pragma unroll
+            for (int i = 0; i < XD; ++i) x_n[i] = 0.0;
+            mc_n = oc_n = mu_n = 0.f;
+            if (st >= nsuper) st = pair;                 // wraps to the first super-tile of the next m-block pass
+            if (st >= nsuper) return;
+            const SuperRef sn = find_super(tk, st);
+            if (et >= sn.nrows) return;
+            const int64_t row = sn.row0 + et;
+#pragma unroll
+            for (int i = 0; i < XD; ++i) x_n[i] = tk.X[sn.t][(tk.begin[sn.t] + row) * XD + i];
+            const float* mw = reinterpret_cast<const float*>(tk.MW[sn.t]) + row;
+            const size_t cap = (size_t)tk.cap[sn.t];
+            mc_n = mw[(size_t)(2 * Q + q) * cap];        // mu^c
+            oc_n = mw[(size_t)(3 * Q + q) * cap];        // omega^c
+            mu_n = mw[(size_t)q * cap];                  // mu
+        };
+        fetch_row(pair);
         for (int jm = 0; jm < njobs; ++jm) {
             const int m = (2 * jm + (int)rank) * kRows + ml;
             float2 nzh[XD], nzl[XD];
@@ -205,21 +228,17 @@ tc_bwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
                 float* rd = rowdat;
                 if (scount > 0) asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");   // previous super-tile fully read
                 {
-                    const bool valid = et < sr.nrows;
-                    const int64_t row = sr.row0 + et;
 #pragma unroll
                     for (int i = 0; i < XD; ++i) {
-                        const double x = valid ? tk.X[sr.t][(tk.begin[sr.t] + row) * XD + i] : 0.0;
                         float h, l;
-                        split_scaled(x, sscale, h, l);
+                        split_scaled(x_n[i], sscale, h, l);
                         rd[i * kSuper + et] = h;
                         rd[(XD + i) * kSuper + et] = l;
                     }
-                    const float* mw = reinterpret_cast<const float*>(tk.MW[sr.t]) + row;
-                    const size_t cap = (size_t)tk.cap[sr.t];
-                    rd[(2 * XD) * kSuper + et] = valid ? mw[(size_t)(2 * Q + q) * cap] : 0.f;       // mu^c
-                    rd[(2 * XD + 1) * kSuper + et] = valid ? mw[(size_t)(3 * Q + q) * cap] : 0.f;   // omega^c
-                    rd[(2 * XD + 2) * kSuper + et] = valid ? mw[(size_t)q * cap] : 0.f;             // mu
+                    rd[(2 * XD) * kSuper + et] = mc_n;
+                    rd[(2 * XD + 1) * kSuper + et] = oc_n;
+                    rd[(2 * XD + 2) * kSuper + et] = mu_n;
+                    fetch_row(st + npairs);
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
                 const uint32_t buf = jc & 1u;
