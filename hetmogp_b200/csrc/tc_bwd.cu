@@ -303,8 +303,9 @@ tc_bwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
             }
         }
     } else if (warp == kMmaWarp) {
-        if (lane == 0 && rank == 0) {
-            // ======================================================= MMA issuer (leader CTA, one thread)
+        if (rank == 0) {
+            // ======================================================= MMA issuer (leader CTA): the whole warp runs the loop, one
+            // elected lane issues (elect_one: the descriptors stay in uniform registers)
             int stage = 0; uint32_t phase = 0, jc = 0;
             for (int jm = 0; jm < njobs; ++jm)
                 for (int64_t st = pair; st < nsuper; st += npairs, ++jc) {
@@ -318,17 +319,21 @@ tc_bwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
                         const uint32_t sa = smem_u32(stage_base + (size_t)stage * kStageBytes);
                         const uint64_t k_hi = desc_sw128(sa), k_lo = desc_sw128(sa + kTile);                 // B: K rows (N)
                         const uint64_t c_hi = desc_sw128(sa + 2 * kTile), c_lo = desc_sw128(sa + 3 * kTile); // A: C block (M)
+                        if (elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < kKB / 16; ++ks) {
-                            const uint64_t adv = (uint64_t)(ks * 2);
-                            mma2_f16(d_tmem, c_hi + adv, k_hi + adv, kIdesc, (kb | ks) ? 1u : 0u);
-                            if (npass >= 2) mma2_f16(d_tmem, c_hi + adv, k_lo + adv, kIdesc, 1u);
-                            if (npass >= 3) mma2_f16(d_tmem, c_lo + adv, k_hi + adv, kIdesc, 1u);
+                            for (int ks = 0; ks < kKB / 16; ++ks) {
+                                const uint64_t adv = (uint64_t)(ks * 2);
+                                mma2_f16(d_tmem, c_hi + adv, k_hi + adv, kIdesc, (kb | ks) ? 1u : 0u);
+                                if (npass >= 2) mma2_f16(d_tmem, c_hi + adv, k_lo + adv, kIdesc, 1u);
+                                if (npass >= 3) mma2_f16(d_tmem, c_lo + adv, k_hi + adv, kIdesc, 1u);
+                            }
+                            commit2(&sb->empty[stage]);
                         }
-                        commit2(&sb->empty[stage]);
+                        __syncwarp();
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
-                    commit2(&sb->tfull[buf]);
+                    if (elect_one()) commit2(&sb->tfull[buf]);
+                    __syncwarp();
                 }
         } else if (lane == 0) {
             // peer CTA: relay stage readiness to the leader

@@ -83,16 +83,27 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
         "r"(cta)
         : "memory");
 }
-// wait on a barrier that peers of the cluster arrive on (acquire at cluster scope)
+// wait on a barrier that peers of the cluster arrive on (acquire at cluster scope).  HM_ISSUER_WAIT 0: hardware-suspended
+// try_wait; 1: no suspend hint -- the one issuing thread spins (0.1-0.2 ms per kernel at cfg3)
+#ifndef HM_ISSUER_WAIT
+#define HM_ISSUER_WAIT 1
+#endif
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     long long t0 = 0;
     for (uint32_t it = 1;; ++it) {
         uint32_t ok;
+#if HM_ISSUER_WAIT == 0
         asm volatile(
             "{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
             : "memory");
+#else
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+#endif
         if (ok) return;
         if ((it & 1023u) == 0) {
             const long long t = clock64();
@@ -100,6 +111,27 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
             else if (t - t0 > 8000000000LL) __trap();
         }
     }
+}
+
+// one non-blocking probe of such a barrier
+__device__ __forceinline__ bool mbar_probe_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+
+// One lane of a converged warp (elect.sync).  The MMA-issuing warps run their loops with all 32 lanes and predicate only
+// the tcgen05 instructions on this: the shared-memory descriptors and TMEM addresses then stay provably warp-uniform and
+// ptxas keeps them in uniform registers.  Issued from inside an `if (lane == 0)` region instead, every UTCHMMA is preceded
+// by seven R2UR moves (~120 cycles of issue per MMA: as long as the MMA itself runs, so the tensor pipe idles at every
+// hiccup).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
 }
 
 // ---------------------------------------------------------------- async proxy / bulk copy

@@ -348,8 +348,9 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
             }
         }
     } else if (warp == kMmaWarp) {
-        // ======================================================= MMA issuer (one thread; leader CTA of a pair)
-        if (lane == 0 && rank == 0) {
+        // ======================================================= MMA issuer (leader CTA of a pair): the whole warp runs the
+        // loop, one elected lane issues (elect_one: the descriptors stay in uniform registers)
+        if (rank == 0) {
             int stage = 0; uint32_t phase = 0, jc = 0;
             for (int64_t st_ = step0; st_ < nsteps; st_ += dstep) {
                 for (int h = 0; h < nhalf; ++h, ++jc) {
@@ -365,23 +366,27 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
                         const uint32_t sa = smem_u32(stage_base + (size_t)stage * kStageBytes);
                         const uint64_t a_hi = desc_sw128(sa), a_lo = desc_sw128(sa + kAHalf);
                         const uint64_t b_hi = desc_sw128(sa + 2 * kAHalf), b_lo = desc_sw128(sa + 2 * kAHalf + kBH);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < kKB / 16; ++ks) {
-                            const uint64_t adv = (uint64_t)(ks * 2);   // 32 bytes per K=16 step, in 16-byte units
-                            if (NCTA == 2) {
-                                mma2_f16(d_tmem, a_hi + adv, b_hi + adv, kIdesc, (kb | ks) ? 1u : 0u);
-                                if (npass >= 2) mma2_f16(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
-                                if (npass >= 3) mma2_f16(d_tmem, a_lo + adv, b_hi + adv, kIdesc, 1u);
-                            } else {
-                                mma_f16(d_tmem, a_hi + adv, b_hi + adv, kIdesc, (kb | ks) ? 1u : 0u);
-                                if (npass >= 2) mma_f16(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
-                                if (npass >= 3) mma_f16(d_tmem, a_lo + adv, b_hi + adv, kIdesc, 1u);
+                            for (int ks = 0; ks < kKB / 16; ++ks) {
+                                const uint64_t adv = (uint64_t)(ks * 2);   // 32 bytes per K=16 step, in 16-byte units
+                                if (NCTA == 2) {
+                                    mma2_f16(d_tmem, a_hi + adv, b_hi + adv, kIdesc, (kb | ks) ? 1u : 0u);
+                                    if (npass >= 2) mma2_f16(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
+                                    if (npass >= 3) mma2_f16(d_tmem, a_lo + adv, b_hi + adv, kIdesc, 1u);
+                                } else {
+                                    mma_f16(d_tmem, a_hi + adv, b_hi + adv, kIdesc, (kb | ks) ? 1u : 0u);
+                                    if (npass >= 2) mma_f16(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
+                                    if (npass >= 3) mma_f16(d_tmem, a_lo + adv, b_hi + adv, kIdesc, 1u);
+                                }
                             }
+                            if (NCTA == 2) commit2(&sb->empty[stage]); else commit(&sb->empty[stage]);   // frees the smem stage
                         }
-                        if (NCTA == 2) commit2(&sb->empty[stage]); else commit(&sb->empty[stage]);   // frees the smem stage
+                        __syncwarp();
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
-                    if (NCTA == 2) commit2(&sb->tfull[buf]); else commit(&sb->tfull[buf]);           // accumulator complete
+                    if (elect_one()) { if (NCTA == 2) commit2(&sb->tfull[buf]); else commit(&sb->tfull[buf]); }   // accumulator complete
+                    __syncwarp();
                 }
             }
         } else if (NCTA == 2 && lane == 0) {
