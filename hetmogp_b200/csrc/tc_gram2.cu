@@ -82,6 +82,16 @@ constexpr int kFoldWarp0 = kGenWarps + 1 + kLoaders;
 constexpr int kThreads = (kGenWarps + 1 + kLoaders + kFoldWarps) * 32;
 static_assert(kFoldWarp0 % 4 == 0, "fold warp w serves TMEM lane quadrant w % 4");
 constexpr uint32_t kAccCols = 256;                 // TMEM columns per accumulator buffer (two buffers: windows alternate)
+#ifndef HM_G2_LGRP
+#define HM_G2_LGRP 2        // chunks per row-loader group
+#endif
+#ifndef HM_G2_TRACE
+#define HM_G2_TRACE 0       // 1: CTA 0 records clock64() at the hand-offs of its first chunks (tools/g2_trace.py)
+#endif
+#ifndef HM_G2_KO
+#define HM_G2_KO 0          // timing experiments (wrong results): 1 generators do nothing but the handshakes, 2 no operand stores,
+                            // 3 no ex2, 4 no hi/lo split
+#endif
 #ifndef HM_G2_CARRY
 #define HM_G2_CARRY 0.75f                          // a window starts at -HM_G2_CARRY times the buffer's previous final value
 #endif
@@ -134,17 +144,28 @@ __device__ __forceinline__ void kgen(const RowX<XD>& r, const float (&zh)[XD], c
             e[p] = fma2(d, d, e[p]);
         }
 #pragma unroll
-    for (int p = 0; p < 4; ++p) kv[p] = make_float2(ex2(-e[p].x), ex2(-e[p].y));
+    for (int p = 0; p < 4; ++p) kv[p] = (HM_G2_KO == 3) ? e[p] : make_float2(ex2(-e[p].x), ex2(-e[p].y));
 }
 
 // split2 of tc_common.cuh that also returns the fp32 residual v - hi (the value the fp16 lo pair rounds)
 __device__ __forceinline__ void split2r(float2 v, uint32_t& hi, uint32_t& lo, float2& r) {
+    if (HM_G2_KO == 4) { hi = __float_as_uint(v.x); lo = __float_as_uint(v.y); r = v; return; }
     const __half2 h = __floats2half2_rn(v.x, v.y);
     r = __fadd2_rn(v, make_float2(-__low2float(h), -__high2float(h)));
     const __half2 l = __floats2half2_rn(r.x, r.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+
+__device__ __forceinline__ void G2_STORE(uint8_t* p, uint4 v) {
+    if (HM_G2_KO != 2 || v.x == 0x12345678u) *reinterpret_cast<uint4*>(p) = v;
+}
+#if HM_G2_TRACE
+__device__ long long g2_trace[8][2048];
+#define G2_TR(k, c) do { if (blockIdx.x == 0 && (c) < 2048u) g2_trace[k][c] = clock64(); } while (0)
+#else
+#define G2_TR(k, c) do { } while (0)
+#endif
 
 template <int XD, int NV>
 __global__ void __launch_bounds__(kThreads, 1)   // 24 warps: 80 registers per thread (the generators, rid of the folds, fit)
@@ -221,7 +242,9 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
                     if (kPhases > 1 && (cc_ % kPhases) != phase) continue;
                     const int stage = cc_ % kStages, rs = cc_ % kRowSlots;
                     mbar_wait_warp(&sb->rowfull[rs], (cc_ / kRowSlots) & 1u);
+                    if (threadIdx.x == 0) G2_TR(0, cc_);
                     mbar_wait_warp(&sb->empty[stage], ((cc_ / kStages) & 1u) ^ 1u);
+                    if (threadIdx.x == 0) G2_TR(1, cc_);
                     const float* rb = rowbuf + (size_t)rs * kC * kRowArrays;   // SoA: array a at rb + a * kC
                     uint8_t* a_hi = stage_base + (size_t)stage * kStageBytes + col * 128;
                     uint8_t* b_hi = a_hi + 2 * kHalf;
@@ -230,7 +253,7 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
                     // instruction descriptor and no per-element sign work is needed.
                     const bool mixed = sflag == 2u;
 #pragma unroll 2
-                    for (int g = 0; g < kGroups; ++g) {
+                    for (int g = 0; g < (HM_G2_KO == 1 ? 0 : kGroups); ++g) {
                         const int n8 = rh * kGroups + g;
                         const int off = (n8 ^ swz) << 4;
                         RowX<XD> r;
@@ -252,7 +275,7 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
 #pragma unroll
                         for (int p = 0; p < 4; ++p) split2r(mul2(kv[p], sw[p]), hi[p], lo[p], res[p]);
                         if (diag) {
-                            *reinterpret_cast<uint4*>(b_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            G2_STORE(b_hi + off, make_uint4(hi[0], hi[1], hi[2], hi[3]));
                             if (HM_G2_SYMDIAG) {
                                 // A diagonal block is symmetric: hh + hl + lh = sym(hh + 2 hl).  The lo operand is stored
                                 // doubled (exact) and only the two products A_hi.B_hi, A_hi.(2 B_lo) are issued; the reduce
@@ -260,7 +283,7 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
 #pragma unroll
                                 for (int p = 0; p < 4; ++p) lo[p] = pack_h2(2.f * res[p].x, 2.f * res[p].y);
                             }
-                            *reinterpret_cast<uint4*>(b_hi + kHalf + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            G2_STORE(b_hi + kHalf + off, make_uint4(lo[0], lo[1], lo[2], lo[3]));
                             // Ah.Bh + Ah.Bl + Al.Bh leaves out Al.Bl.  Between different inducing points the residuals are
                             // uncorrelated; on the diagonal entry both operands are the same value, the term is sgn . lo^2
                             // every row, and K_uu^-1 . K_uu^-1 amplifies that 1e-7-relative diagonal bias to several 1e-3
@@ -286,19 +309,19 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
                                     cacc = fma2(t, res[p], cacc);
                                 }
                             }
-                            *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0] ^ sgn.x, hi[1] ^ sgn.y, hi[2] ^ sgn.z, hi[3] ^ sgn.w);
+                            G2_STORE(a_hi + off, make_uint4(hi[0] ^ sgn.x, hi[1] ^ sgn.y, hi[2] ^ sgn.z, hi[3] ^ sgn.w));
                             if (!(HM_G2_SYMDIAG && diag))
-                                *reinterpret_cast<uint4*>(a_hi + kHalf + off) = make_uint4(lo[0] ^ sgn.x, lo[1] ^ sgn.y, lo[2] ^ sgn.z, lo[3] ^ sgn.w);
+                                G2_STORE(a_hi + kHalf + off, make_uint4(lo[0] ^ sgn.x, lo[1] ^ sgn.y, lo[2] ^ sgn.z, lo[3] ^ sgn.w));
                         } else if (!diag || !HM_G2_ALIAS) {
-                            *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                            *reinterpret_cast<uint4*>(a_hi + kHalf + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            G2_STORE(a_hi + off, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+                            G2_STORE(a_hi + kHalf + off, make_uint4(lo[0], lo[1], lo[2], lo[3]));
                         }
                         if (!diag) {
                             kgen<XD>(r, bzh, bzl, bnb, kv);
 #pragma unroll
                             for (int p = 0; p < 4; ++p) split2r(mul2(kv[p], sw[p]), hi[p], lo[p], res[p]);
-                            *reinterpret_cast<uint4*>(b_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                            *reinterpret_cast<uint4*>(b_hi + kHalf + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            G2_STORE(b_hi + off, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+                            G2_STORE(b_hi + kHalf + off, make_uint4(lo[0], lo[1], lo[2], lo[3]));
                         }
                     }
                     fence_async_smem();
@@ -307,6 +330,7 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
                         if ((warp % kPhaseWarps) == 0) sb->sflag[stage] = sflag;   // ordered before the MMA issuer's read by the barrier
                         mbar_arrive(&sb->full[stage]);
                         mbar_arrive(&sb->rowempty[rs]);
+                        if (threadIdx.x == 0) G2_TR(2, cc_);
                     }
                 }
                 if (NV > 0 && sg.has_g) { g64 += (double)(g2.x + g2.y); g2 = dup2(0.f); }   // fp32 partial per window
@@ -390,7 +414,9 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
                     fence_after();
                     for (int c = c0; c < c1; ++c, ++cc_) {
                         const int stage = cc_ % kStages;
+                        G2_TR(3, cc_);
                         mbar_wait_cluster(&sb->full[stage], (cc_ / kStages) & 1u);
+                        G2_TR(4, cc_);
                         fence_after();
                         const uint32_t sa = smem_u32(stage_base + (size_t)stage * kStageBytes);
                         // sign class of the chunk's weights: uniform -> A is the unsigned operand, negated by the instruction if the
@@ -409,7 +435,9 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
                             if (npass >= 3 && !(HM_G2_SYMDIAG && diag)) mma2_f16(d_tmem, a_lo + adv, b_hi + adv, idc, 1u);
                             if (npass >= 4) mma2_f16(d_tmem, a_lo + adv, b_lo + adv, idc, 1u);   // diagnostic
                         }
+                        G2_TR(5, cc_);
                         commit2(&sb->empty[stage]);
+                        G2_TR(6, cc_);
                     }
                     commit2(&sb->accfull[buf]);
                     ++iv;
@@ -432,7 +460,8 @@ tc_gram2_kernel(HmTasks tk, HmProjArgs pa, const HmTcInfo* __restrict__ info, co
         // Each iteration issues the global loads of 2 chunks (128 rows) before touching the ring: memory-level
         // parallelism instead of one exposed HBM/L2 latency per chunk.  Both CTAs of a pair stage the same rows.
         // (One loader warp caps the kernel at ~3400 cycles per chunk: fp64 input splits, sqrt, sign words.)
-        constexpr int kGrp = 2;
+        constexpr int kGrp = HM_G2_LGRP;
+        static_assert(kGrp * kLoaders <= kRowSlots, "a loader must stay within one lap of the row ring (mbarrier parity)");
         const int rw = warp - (kMmaWarp + 1);
         uint32_t grp = 0;
         int nch[HM_MAXT];
@@ -613,3 +642,9 @@ int hm_tc_gram2_reduce(cudaStream_t s, const double* slots, const HmGramJob* job
     HM_CUDA(cudaGetLastError());
     return 0;
 }
+
+#if HM_G2_TRACE
+extern "C" int hmogp_debug_g2_trace(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, g2_trace, sizeof(long long) * 8 * 2048);
+}
+#endif
