@@ -159,6 +159,14 @@ __global__ void __launch_bounds__(128) chol_panel_kernel(double* A, int ld, int6
     __shared__ double invd[NB];   // 1 / D[j][j]: fp64 division and square root are ~350-cycle dependent sequences, and the
                                   // panel is one long dependent chain of them; one rsqrt per pivot, multiplications elsewhere
     const int tid = threadIdx.x;
+    // the panel row this thread solves is requested first: its HBM/L2 round trip overlaps the diagonal block's factorisation
+    const int row = k0 + blockIdx.x * 128 + tid;
+    double* arow = A + (int64_t)row * ld + k0;
+    double x[NB];
+    if (row < n && row >= k0 + NB) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) x[j] = arow[j];
+    }
     for (int e = tid; e < NB * NB; e += 128) {
         const int i = e / NB, j = e % NB;
         D[i][j] = A[(int64_t)(k0 + i) * ld + k0 + j];
@@ -196,16 +204,11 @@ __global__ void __launch_bounds__(128) chol_panel_kernel(double* A, int ld, int6
         for (int j = 0; j < NB; ++j) D[lane][j] = (j <= lane) ? a[j] : 0.0;
     }
     __syncthreads();
-    const int row = k0 + blockIdx.x * 128 + tid;
     if (row >= n) return;
-    double* arow = A + (int64_t)row * ld + k0;
     if (row < k0 + NB) {
         const int i = row - k0;
         for (int j = 0; j < NB; ++j) arow[j] = (j <= i) ? D[i][j] : 0.0;
     } else {
-        double x[NB];
-#pragma unroll
-        for (int j = 0; j < NB; ++j) x[j] = arow[j];
 #pragma unroll
         for (int j = 0; j < NB; ++j) {   // four independent partial sums per entry
             double s0 = x[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -248,7 +251,6 @@ __global__ void __launch_bounds__(64) triinv_diag_kernel(const double* __restric
     const int o = blockIdx.x * NB;
     extern __shared__ double triinv_smem[];
     double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(triinv_smem);
-    double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(triinv_smem + NB * (NB + 1));
     for (int e = threadIdx.x; e < NB * NB; e += 64) {
         const int i = e / NB, j = e % NB;
         Ls[i][j] = L[(int64_t)(o + i) * ld + o + j];
@@ -258,35 +260,29 @@ __global__ void __launch_bounds__(64) triinv_diag_kernel(const double* __restric
     __shared__ double rdiag[NB];   // reciprocal diagonal, computed in parallel: no division in the serial sweep below
     rdiag[c] = 1.0 / Ls[c][c];
     __syncthreads();
+    // Thread c solves L x = e_c by forward substitution with x in REGISTERS (fully unrolled: 2016 FMAs on broadcast loads of
+    // L; entries above the diagonal come out as exact zeros, so control flow is uniform).  The version this replaces kept x
+    // in shared memory and walked dependent load -> FMA chains: 45-60 us for the 64 x 64 blocks, on the critical path of the
+    // prepare chain.
+    double x[NB];
+#pragma unroll
     for (int i = 0; i < NB; ++i) {
-        double v;
-        if (i < c) v = 0.0;
-        else if (i == c) v = rdiag[c];
-        else {   // four independent partial sums (the chain of dependent shared-memory FMAs dominated this kernel)
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int l = c;
-            for (; l + 4 <= i; l += 4) {
-                s0 += Ls[i][l] * Xs[l][c];
-                s1 += Ls[i][l + 1] * Xs[l + 1][c];
-                s2 += Ls[i][l + 2] * Xs[l + 2][c];
-                s3 += Ls[i][l + 3] * Xs[l + 3][c];
-            }
-            for (; l < i; ++l) s0 += Ls[i][l] * Xs[l][c];
-            v = -((s0 + s1) + (s2 + s3)) * rdiag[i];
+        double s0 = (i == c) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int l = 0; l < i; ++l) {
+            const double p = Ls[i][l] * x[l];
+            if ((l & 3) == 0) s0 -= p; else if ((l & 3) == 1) s1 -= p; else if ((l & 3) == 2) s2 -= p; else s3 -= p;
         }
-        Xs[i][c] = v;
+        x[i] = ((s0 + s1) + (s2 + s3)) * rdiag[i];
     }
-    __syncthreads();
-    for (int e = threadIdx.x; e < NB * NB; e += 64) {
-        const int i = e / NB, j = e % NB;
-        X[(int64_t)(o + i) * ld + o + j] = Xs[i][j];
-    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) X[(int64_t)(o + i) * ld + o + c] = (i >= c) ? x[i] : 0.0;
 }
 
 int hm_tri_inverse(cudaStream_t s, const double* L, double* X, double* tmp, int Mp, int64_t sQ, int Q) {
     HM_CUDA(cudaMemsetAsync(X, 0, sizeof(double) * sQ * Q, s));
     dim3 grid((unsigned)(Mp / 64), (unsigned)Q);
-    const int triinv_bytes = 2 * 64 * 65 * (int)sizeof(double);
+    const int triinv_bytes = 64 * 65 * (int)sizeof(double);
     HM_CUDA(cudaFuncSetAttribute(triinv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, triinv_bytes));
     triinv_diag_kernel<<<grid, 64, triinv_bytes, s>>>(L, X, Mp, sQ);
     HM_CUDA(cudaGetLastError());

@@ -148,8 +148,8 @@ def _assert_chain(err, tol_ve):
 def test_benchmark_shape_against_oracle():
     """The benchmark's configuration (cfg3: M=500, Q=3, five likelihoods, cond(K_uu) up to 2e3) at N = 2e4 rows per output
     against the CPU oracle directly (one oracle evaluation, ~25 s), in the shipped tensor-core mode and in fp64.
-    Measured on B200 (profiles/r02_oracle_check.txt): tc ELBO 2.4e-6, VE 2.6e-6, dL_dmu_u 2.4e-4, dL_dL_u 2e-3, dL_dKmm 5e-3,
-    d_rbf 5e-4, dW 2.5e-4, dkappa 3.5e-6, dZ 5e-3 .. 1.1e-2; K_uu / L / K_uu^-1 1.6e-11 / 2.1e-10 / 4.3e-9.
+    Measured on B200 (profiles/r2_oracle_check.txt): tc ELBO 2.4e-6, VE 2.6e-6, dL_dmu_u 2.4e-4, dL_dL_u 9.2e-4, dL_dKmm 2.3e-3,
+    d_rbf 7.9e-4, dW 2.5e-4, dkappa 3.5e-6, dZ 3.2e-3; K_uu / L / K_uu^-1 1.6e-11 / 2.1e-10 / 4.3e-9.
     The blocks that pass through K_uu^-1 H K_uu^-1 (dL_dL_u, dL_dKmm, dZ) carry the fp32-class error of the row
     quantities amplified by cond(K_uu): the fp32 SIMT mode measures 4e-3 / 9e-3 / 1.4e-2 on the same problem."""
     prob = synth.make_config("cfg3", N=20000)
@@ -161,7 +161,7 @@ def test_benchmark_shape_against_oracle():
     _assert_chain(err, 1e-10)
     err, _, _ = pu.compare(prob, "tc", oracle_out=o)
     assert err["elbo"] < 1e-5
-    tol = dict(dL_dmu_u=1e-3, dL_dL_u=6e-3, dL_dKmm=1.2e-2, d_rbf=2e-3, dW=1e-3, dkappa=1e-4, dZ=2e-2)
+    tol = dict(dL_dmu_u=1e-3, dL_dL_u=3e-3, dL_dKmm=6e-3, d_rbf=2e-3, dW=1e-3, dkappa=1e-4, dZ=1e-2)
     for k, t in tol.items():
         assert err[k] < t, (k, err[k])
     _assert_chain(err, 1e-6)
