@@ -66,7 +66,9 @@ tc_bwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
     const int Mc = pa.Mc, Mp = pa.Mp, M = pa.M, Q = pa.Q;
     const int q = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb = Mc / kKB, njobs = Mc / 256;             // pair jobs: m-blocks (2 jm, 2 jm + 1)
+    // k blocks of 64 inducing points: `nkbf` in the operand image (padded M), `nkb` worth contracting over (K is exactly
+    // zero on padded inducing points); pair jobs: m-blocks (2 jm, 2 jm + 1)
+    const int nkbf = Mc / kKB, nkb = (M + kKB - 1) / kKB, njobs = Mc / 256;
     const uint32_t rank = cluster_ctarank();
     const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
@@ -357,7 +359,7 @@ tc_bwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
                     for (int kb = 0; kb < nkb; ++kb) {
                         mbar_wait(&sb->empty[stage], phase ^ 1);
                         uint8_t* dst = stage_base + (size_t)stage * kStageBytes + 2 * kTile;
-                        const uint8_t* src = reinterpret_cast<const uint8_t*>(Cb) + ((size_t)(q * nhalf + jm) * nkb + kb) * (2 * kCHalf) + rank * kTile;
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(Cb) + ((size_t)(q * nhalf + jm) * nkbf + kb) * (2 * kCHalf) + rank * kTile;
                         mbar_expect_tx(&sb->full[stage], 2 * kTile);
                         bulk_g2s(dst, src, kTile, &sb->full[stage]);                    // hi
                         bulk_g2s(dst + kTile, src + kCHalf, kTile, &sb->full[stage]);   // lo

@@ -141,7 +141,9 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
     const int Mc = pa.Mc, Mp = pa.Mp, M = pa.M, Q = pa.Q;
     const int q = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nhalf = Mc / kNB, nkb = Mc / kKB;
+    // k blocks of 64 inducing points: `nkbf` in the operand image (padded M), `nkb` worth contracting over -- K and C are
+    // exactly zero on padded inducing points, so the blocks beyond M are skipped (M = 64: one of four)
+    const int nhalf = Mc / kNB, nkbf = Mc / kKB, nkb = (M + kKB - 1) / kKB;
 
     uint8_t* stage_base = smem;                                                   // kStages * 96 KB, 1024-aligned
     float* tab = reinterpret_cast<float*>(smem + kStages * kStageBytes);          // [Mc/8][R][8]
@@ -283,6 +285,7 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
                 const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + buf * kNB + ch * (kNB / 2);
 #pragma unroll 1
                 for (int cc = 0; cc < kNB / 64; ++cc) {
+                    if (h * kNB + ch * (kNB / 2) + cc * 32 >= M) break;   // padded columns: K = 0 there, every sum gets exactly 0
                     uint32_t v[32];
                     tmem_ld32(taddr + cc * 32, v);
                     tmem_ld_wait();
@@ -409,7 +412,7 @@ tc_fwd_kernel(HmTasks tk, HmProjArgs pa, const uint16_t* __restrict__ Cb, const 
                     for (int kb = 0; kb < nkb; ++kb) {
                         mbar_wait(&sb->empty[stage], phase ^ 1);
                         uint8_t* dst = stage_base + (size_t)stage * kStageBytes + 2 * kAHalf;
-                        const uint8_t* src = reinterpret_cast<const uint8_t*>(Cb) + ((size_t)(q * nhalf + h) * nkb + kb) * (2 * kBHalf) + rank * kBH;
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(Cb) + ((size_t)(q * nhalf + h) * nkbf + kb) * (2 * kBHalf) + rank * kBH;
                         mbar_expect_tx(&sb->full[stage], 2 * kBH);
                         bulk_g2s(dst, src, kBH / 2, &sb->full[stage]);                                   // hi
                         bulk_g2s(dst + kBH / 2, src + kBH / 2, kBH / 2, &sb->full[stage]);
