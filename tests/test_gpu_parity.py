@@ -104,6 +104,10 @@ CASES = {
     "pad_m300": dict(liks=[("Gaussian", 0.5), ("Bernoulli",), ("Poisson",)], N=2500, M=300, Q=3, Xdim=1),
     "ragged_x2": dict(liks=[("Categorical", 4), ("Gaussian", 0.5)], N=[1500, 1], M=100, Q=2, Xdim=2, kappa_scale=1.0),
     "m513": dict(liks=[("Bernoulli",)], N=700, M=513, Q=1, Xdim=1),
+    # small M inside one 256-wide tile: the projection kernels contract over ceil(M / 64) k-blocks only and the forward
+    # epilogue stops at column M (M = 64: one block, exactly full; M = 130: three blocks, the last one two columns wide)
+    "m64": dict(liks=[("Gaussian", 0.5), ("Poisson",)], N=[900, 333], M=64, Q=2, Xdim=1),
+    "m130_x2": dict(liks=[("Bernoulli",), ("Gaussian", 0.5)], N=[700, 200], M=130, Q=2, Xdim=2, ls_factor=(0.8, 0.9)),
     # padded M a multiple of 256: the CTA-pair Gram kernel (tc_gram2.cu) with Xdim = 2 / 3, ragged tasks, three block rows
     "pair_m200_x2": dict(liks=[("Gamma",), ("Beta",), ("Gaussian", 0.5)], N=[1500, 700, 3], M=200, Q=2, Xdim=2),
     "pair_m700_x3": dict(liks=[("Bernoulli",), ("Poisson",)], N=[900, 130], M=700, Q=1, Xdim=3),
