@@ -1016,7 +1016,7 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
         e->gram2 = !(eg && atoi(eg) == 1) && e->Mc % 256 == 0 && e->nworkers >= 2;
         e->gram_chunk = e->gram2 ? HM_GRAM2_CHUNK : HM_GRAM_CHUNK;
         eg = getenv("HMOGP_TC_GRAM_DIAG_COST");
-        e->gram2_cost_diag = eg ? atoi(eg) : 75;   // a diagonal block generates one operand tile instead of two (generation, not the MMAs, sets the pace)
+        e->gram2_cost_diag = eg ? atoi(eg) : 75;   // plan weight of a diagonal block against an off-diagonal one (two MMA products + one generated operand tile instead of three + two; measured optimum)
         e->tc_f1 = (ev ? atoi(ev) : (e->gram2 ? 1024 : 512)) / e->gram_chunk;   // pair kernel: one window per TMEM buffer, folded straight into fp64
         if (e->tc_f1 < 1) e->tc_f1 = 1;
         ev = getenv("HMOGP_TC_FLUSH3_ROWS");         // rows between fp64 flushes
