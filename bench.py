@@ -430,6 +430,12 @@ def main():
                       "elbo": abs(float(o_t["log_marginal"][0, 0] - o_r["log_marginal"][0, 0])) / abs(float(o_r["log_marginal"][0, 0]))}
             for k in ("dL_dmu_u", "dL_dL_u", "dL_dKmm", "d_rbf", "dW", "dkappa", "dZ"):
                 parity[k] = rel(k)
+            # d_rbf by column: RBF variances (their K_mm part comes from traces against K_uu^-1 and per-row sums)
+            # and lengthscales (through K_uu^-1 H K_uu^-1: the most amplified entry of the whole gradient)
+            for j, nm in ((0, "d_rbf_variance"), (1, "d_rbf_lengthscale")):
+                a_, b_ = o_t["d_rbf"][:, j], o_r["d_rbf"][:, j]
+                parity[nm] = float((a_ - b_).abs().max() / b_.abs().max())
+                parity[nm + "_per_latent"] = [float(x) for x in ((a_ - b_).abs() / b_.abs())]
         except Exception as e:
             parity = {"error": repr(e)}
 

@@ -244,11 +244,49 @@ __global__ void kmm_grad_kernel(const double* dLdK, const double* Zp, const HmCo
     }
 }
 
+// Per latent q, fixed-order sums over the real M x M block (one CTA per q):
+//   tr[q][0] = sum_ij H_ij Ki_ij = tr(H K_uu^-1),  [1] = tr(S K_uu^-1),  [2] = g1 . alpha,  [3] = m . alpha
+// These give sum_ij K_uu o dL/dK_mm -- the K_mm part of the RBF variance gradient (svmogp.py:116) -- WITHOUT going through
+// E = K_uu^-1 H K_uu^-1: with K_uu K_uu^-1 = I,
+//   sum K_uu o dL/dK = -tr(H K^-1) - 2 tr(H C) - g1.alpha - M/2 + tr(S K^-1)/2 + m.alpha/2,   tr(H C) = sum_n omega_n c_n,
+// where the last is a sum of per-row quantities the forward pass already produced.  H enters once against K_uu^-1 instead
+// of twice: its error is amplified by cond(K_uu) instead of cond^1.4+ (tensor-core mode, cfg3: 3.5e-2 -> see DESIGN.md).
+constexpr int kTraceSlices = 32;
+__global__ void kmm_trace_kernel(const double* __restrict__ H, const double* __restrict__ Ki, const double* __restrict__ S,
+                                 const double* __restrict__ g1, const double* __restrict__ alpha, const double* __restrict__ mp,
+                                 double* tr, int M, int Mp) {
+    const int q = blockIdx.y, sl = blockIdx.x, tid = threadIdx.x;    // slice sl: rows sl, sl + 32, ... (partials, summed in
+    const int64_t b = (int64_t)q * Mp * Mp;                           // slice order by assemble_scalar_kernel)
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = sl; i < M; i += kTraceSlices)
+        for (int j = tid; j < M; j += blockDim.x) {
+            const int64_t ij = b + (int64_t)i * Mp + j;
+            const double ki = Ki[ij];
+            t[0] += H[ij] * ki;
+            t[1] += S[ij] * ki;
+        }
+    if (sl == 0)
+        for (int i = tid; i < M; i += blockDim.x) {
+            const double al = alpha[(int64_t)q * Mp + i];
+            t[2] += g1[(int64_t)q * Mp + i] * al;
+            t[3] += mp[(int64_t)q * Mp + i] * al;
+        }
+    __shared__ double sh[4][256];
+    for (int k = 0; k < 4; ++k) sh[k][tid] = t[k];
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (tid < w) for (int k = 0; k < 4; ++k) sh[k][tid] += sh[k][tid + w];
+        __syncthreads();
+    }
+    if (tid < 4) tr[(q * kTraceSlices + sl) * 4 + tid] = sh[tid][0];
+}
+
 struct AssembleArgs {
     int M, Mp, Q, J, T, Xd, what;
     const double* stats;
     int off_sdv, off_sma, off_svc, off_dls, off_g1, off_dz;
     const double *KLq, *kg, *alpha, *dLdLfull, *dLdK, *rowstat, *dzmm;
+    const double *tr, *jitter;   // kmm_trace_kernel sums (nullptr: not used) and the jitter K_uu^q was factored with
     const HmConsts* c;
     // outputs (device staging, reference layouts)
     double *log_marginal, *VE, *KL, *dmu, *dL, *dKmm, *drbf, *dW, *dkappa, *dZ;
@@ -287,6 +325,15 @@ __global__ void assemble_scalar_kernel(AssembleArgs a) {
             s1 += __shfl_down_sync(0xffffffffu, s1, w);
         }
         if (lane != 0) return;
+        if (a.tr && a.jitter[q] == 0.0) {
+            // sum K_uu o dL/dK_mm through traces (kmm_trace_kernel); with jitter K_uu K_uu^-1 != I and the direct sum stays
+            double hc = 0.0;
+            for (int d = 0; d < a.J; ++d) hc += c->W[d][q] * c->W[d][q] * svc[d * a.Q + q];   // tr(H C) = sum_n omega_n c_n
+            double t[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int sl = 0; sl < kTraceSlices; ++sl)
+                for (int k = 0; k < 4; ++k) t[k] += a.tr[(q * kTraceSlices + sl) * 4 + k];
+            s0 = -t[0] - 2.0 * hc - t[2] - 0.5 * a.M + 0.5 * t[1] + 0.5 * t[3];
+        }
         double dvar = s0 / c->var[q];   // update_gradients_full(dL_dKmm, Z_q)   svmogp.py:116
         double dls = s1 / c->ls[q];
         double kmn = 0.0, kd = 0.0;
@@ -411,7 +458,7 @@ struct hmogp_engine {
     double* slots;         // [nslots][HM_GRAM_SLOT_DOUBLES] fp64 partial tiles
     double* gvec;          // [HM_GRAM_MAXV][Q][Mp]
     bool plan_dirty;
-    double *KLq, *KLpart, *jitter_d, *rowstat, *dzmm;
+    double *KLq, *KLpart, *jitter_d, *rowstat, *dzmm, *trq;
     cudaStream_t s2;          // side stream of the prepare phase (S, S^-1 branch)
     cudaEvent_t ev_fork, ev_S, ev_Sinv;
     cudaGraphExec_t chol_graph;   // the 2 Mp / 32 panel + update launches of the blocked Cholesky, captured once
@@ -424,6 +471,7 @@ struct hmogp_engine {
     // K_uu, its Cholesky factor, the inverses: valid for the (Z, sigma^2, l) in kuu_key_h (host callers) or, for device
     // callers, on the caller's word (hmogp_hint_hyper_unchanged)
     bool kuu_valid, kuu_key_ok, hint_unchanged, kuu_cache_off;
+    bool trace_off;   // HMOGP_NO_KMM_TRACE=1: the RBF variance gradient sums K_uu o dL/dK_mm directly (diagnostic)
     std::vector<double> kuu_key_h;
     long long kuu_reused;
     long long prepA_launches, prepB_launches;
@@ -1048,7 +1096,7 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
         if (!rc && cudaMemcpy(e->jobs_d, e->jobs_h.data(), sizeof(HmGramJob) * nj, cudaMemcpyHostToDevice) != cudaSuccess) rc = HMOGP_ERR_CUDA;
         if (!rc && cudaMemset(e->tcinfo, 0, sizeof(HmTcInfo)) != cudaSuccess) rc = HMOGP_ERR_CUDA;
     }
-    A_(KLq, HM_MAXQ); A_(KLpart, HM_MAXQ * 64); A_(jitter_d, HM_MAXQ); A_(rowstat, Q * Mp * 2); A_(dzmm, Q * Xd * Mp); A_(flags_d, 2 * HM_MAXQ);
+    A_(KLq, HM_MAXQ); A_(KLpart, HM_MAXQ * 64); A_(jitter_d, HM_MAXQ); A_(rowstat, Q * Mp * 2); A_(trq, 4 * kTraceSlices * HM_MAXQ); A_(dzmm, Q * Xd * Mp); A_(flags_d, 2 * HM_MAXQ);
     // statistics layout
     e->off_nneg = (int)T; e->off_sdv = 2 * (int)T; e->off_sma = e->off_sdv + J; e->off_svc = e->off_sma + J * (int)Q;
     e->off_dls = e->off_svc + J * (int)Q; e->off_g1 = e->off_dls + (int)Q; e->off_dz = e->off_g1 + (int)(Q * Mp);
@@ -1075,6 +1123,7 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
     e->prepA_graph = e->prepB_graph = e->prepR_graph = nullptr; e->prepA_launches = e->prepB_launches = e->prepR_launches = 0; e->prepare_calls = 0;
     e->kuu_valid = e->kuu_key_ok = e->hint_unchanged = false; e->kuu_reused = 0;
     { const char* v = getenv("HMOGP_NO_KUU_CACHE"); e->kuu_cache_off = v && atoi(v) != 0; }
+    { const char* v = getenv("HMOGP_NO_KMM_TRACE"); e->trace_off = v && atoi(v) != 0; }
     { const char* v = getenv("HMOGP_NO_GRAPH"); e->graphs_off = v && atoi(v) != 0; }
     for (int t = 0; t < HM_MAXT; ++t) e->up_X[t] = e->up_Y[t] = nullptr;
     if (!rc && (cudaStreamCreateWithFlags(&e->s2, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1257,6 +1306,7 @@ int hmogp_step_finish(hmogp_engine* e, const double* stats_dev, hmogp_grads* g, 
     a.off_g1 = e->off_g1; a.off_dz = e->off_dz;
     a.KLq = e->KLq; a.kg = e->kg; a.alpha = e->alpha; a.dLdLfull = e->dLdLfull; a.dLdK = e->dLdK; a.rowstat = e->rowstat;
     a.dzmm = e->dzmm; a.c = e->consts;
+    a.tr = (what >= HMOGP_WHAT_FULL && !e->trace_off) ? e->trq : nullptr; a.jitter = e->jitter_d;
     a.log_marginal = e->o_lm; a.VE = e->o_VE; a.KL = e->o_KL; a.dmu = e->o_dmu; a.dL = e->o_dL;
     a.dKmm = (g->dL_dKmm || what >= HMOGP_WHAT_FULL) ? e->o_dKmm : nullptr;
     a.drbf = e->o_drbf; a.dW = e->o_dW; a.dkappa = e->o_dkappa; a.dZ = e->o_dZ;
@@ -1284,6 +1334,10 @@ int hmogp_step_finish(hmogp_engine* e, const double* stats_dev, hmogp_grads* g, 
                 dim3 gr((unsigned)hm_cdiv(M, 8), (unsigned)Q);
                 kmm_grad_kernel<<<gr, 256, 0, cs>>>(e->dLdK, e->Zp, e->consts, e->rowstat, e->dzmm, M, Mp, Xd);
                 HM_CUDA(cudaGetLastError());
+                if (a.tr) {
+                    kmm_trace_kernel<<<dim3(kTraceSlices, (unsigned)Q), 256, 0, cs>>>(stats + e->off_H, e->Ki, e->S, stats + e->off_g1, e->alpha, e->mp, e->trq, M, Mp);
+                    HM_CUDA(cudaGetLastError());
+                }
             }
         }
         assemble_scalar_kernel<<<1, 256, 0, cs>>>(a);
