@@ -1061,7 +1061,10 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
         if (e->nworkers < 2) e->tc_ncta = 1;
         ev = getenv("HMOGP_TC_FLUSH_ROWS");          // level-1 (tensor-core fp32) accumulation window
         const char* eg = getenv("HMOGP_TC_GRAM_CTAS");   // 2 (default): CTA-pair Gram when the padded M is a multiple of 256
-        e->gram2 = !(eg && atoi(eg) == 1) && e->Mc % 256 == 0 && e->nworkers >= 2;
+        // M <= 128: one 128 x 128 tile per latent on the one-CTA kernel (every SM its own chunks) instead of a 256 x 256 block
+        // per CTA pair that is three quarters padding
+        const bool small_m = cfg->M <= 128 && !(eg && atoi(eg) == 2);
+        e->gram2 = !(eg && atoi(eg) == 1) && e->Mc % 256 == 0 && e->nworkers >= 2 && !small_m;
         e->gram_chunk = e->gram2 ? HM_GRAM2_CHUNK : HM_GRAM_CHUNK;
         eg = getenv("HMOGP_TC_GRAM_DIAG_COST");
         e->gram2_cost_diag = eg ? atoi(eg) : 75;   // plan weight of a diagonal block against an off-diagonal one (two MMA products + one generated operand tile instead of three + two; measured optimum)
@@ -1084,6 +1087,7 @@ int hmogp_create(const hmogp_config* cfg, hmogp_engine** out) {
         } else
         for (int I = 0; I < e->Mc / 128; ++I)
             for (int j0 = 0; j0 < (I + 1) * 128; j0 += 256) {
+                if (128 * I >= e->M || j0 >= e->M) continue;     // tiles that hold only padding (H is zeroed before the reduce)
                 HmGramJob jb; jb.I = I; jb.j0 = j0; jb.nw = ((I + 1) * 128 - j0) < 256 ? ((I + 1) * 128 - j0) : 256;
                 e->jobs_h.push_back(jb);
             }
